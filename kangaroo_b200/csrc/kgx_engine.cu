@@ -1,0 +1,324 @@
+// kgx_engine.cu -- host side of the B200 jump engine behind the C ABI of include/kgx.h.
+//
+// Replaces the host half of the reference's GPU/GPUEngine.cu (ctor/dtor :144-263, SetKangaroos/GetKangaroos/
+// SetKangaroo :381-538, callKernel :540-557, SetParams :559-590, Launch :607-679) with a stream-ordered
+// design: one non-blocking stream per engine, device-side pack/unpack kernels instead of per-block host
+// transposes, double-buffered DP slabs so the readback of launch i overlaps launch i+1, CUDA-event timing of
+// every launch.  No CPU fallback exists: every entry point fails when CUDA does.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <unistd.h>
+#include "../../include/kgx.h"
+#include "kgx_kernel.cuh"
+
+using namespace kgx;
+
+static char g_create_err[256] = "";
+
+struct kgx_engine {
+  int dev = 0, groups = 0, tpg = 0, sms = 0;
+  u64 n = 0, nPadded = 0;
+  u32 numTiles = 0, maxFound = 0;
+  int nRun = KGX_NB_RUN;
+  uint4* state = nullptr;
+  u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
+  u32* slabPinned = nullptr;
+  u32* jtab = nullptr;
+  uint4 *stgX = nullptr, *stgY = nullptr, *stgD = nullptr;   // device staging (AoS, kIdx order)
+  u64 dpMask = 0;
+  bool haveParams = false, inflight = false;
+  int cur = 0;                 // slab the in-flight (or last) launch writes
+  int done = -1;               // slab of the most recently completed launch
+  cudaStream_t stream = nullptr, copyStream = nullptr;
+  cudaEvent_t evStart[2] = {nullptr, nullptr}, evStop[2] = {nullptr, nullptr};
+  float lastMs = 0.f;
+  u64 launches = 0;
+  size_t slabBytes = 0, stateBytes = 0;
+  char err[256] = "";
+};
+
+#define CK(e, call)                                                                            \
+  do {                                                                                         \
+    cudaError_t _s = (call);                                                                   \
+    if (_s != cudaSuccess) {                                                                   \
+      snprintf((e)->err, sizeof((e)->err), "%s: %s", #call, cudaGetErrorString(_s));           \
+      return -1;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+extern "C" {
+
+int kgx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int kgx_grid_default(int dev, int* x, int* y) {
+  if (*x > 0 && *y > 0) return 0;
+  int n = kgx_device_count();
+  if (n == 0 || dev >= n) return -1;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+  if (*x <= 0) *x = 2 * prop.multiProcessorCount;   // GPUEngine.cu:301
+  if (*y <= 0) *y = 128;                            // GPUEngine.cu:303 (sm_100 is not in the reference's core table)
+  return 0;
+}
+
+int kgx_device_info(int dev, char* buf, int buflen) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+  snprintf(buf, buflen, "%s|%d|%d|%d|%.1f", prop.name, prop.multiProcessorCount, prop.major, prop.minor,
+           (double)prop.totalGlobalMem / 1048576.0);
+  return 0;
+}
+
+const char* kgx_last_error(kgx_engine* e) { return e ? e->err : g_create_err; }
+
+void kgx_destroy(kgx_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->dev);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->state); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
+  cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
+  if (e->slabPinned) cudaFreeHost(e->slabPinned);
+  for (int i = 0; i < 2; i++) { if (e->evStart[i]) cudaEventDestroy(e->evStart[i]); if (e->evStop[i]) cudaEventDestroy(e->evStop[i]); }
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->copyStream) cudaStreamDestroy(e->copyStream);
+  delete e;
+}
+
+kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_found) {
+  kgx_engine* e = new kgx_engine();
+  auto fail = [&](const char* what, cudaError_t s) -> kgx_engine* {
+    snprintf(g_create_err, sizeof g_create_err, "kgx_create: %s: %s", what, cudaGetErrorString(s));
+    kgx_destroy(e);
+    return nullptr;
+  };
+  if (groups <= 0 || threads_per_group <= 0 || max_found == 0) {
+    snprintf(g_create_err, sizeof g_create_err, "kgx_create: bad arguments");
+    delete e; return nullptr;
+  }
+  int cnt = 0;
+  cudaError_t s = cudaGetDeviceCount(&cnt);
+  if (s != cudaSuccess || cnt == 0) {
+    snprintf(g_create_err, sizeof g_create_err, "kgx_create: no CUDA device (%s)", cudaGetErrorString(s));
+    cudaGetLastError(); delete e; return nullptr;
+  }
+  if ((s = cudaSetDevice(dev)) != cudaSuccess) return fail("cudaSetDevice", s);
+  cudaDeviceProp prop;
+  if ((s = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return fail("cudaGetDeviceProperties", s);
+  e->dev = dev; e->groups = groups; e->tpg = threads_per_group; e->sms = prop.multiProcessorCount;
+  e->n = (u64)groups * (u64)threads_per_group * KGX_GPU_GRP_SIZE;
+  e->numTiles = (u32)((e->n + TILE - 1) / TILE);
+  e->nPadded = (u64)e->numTiles * TILE;
+  e->maxFound = max_found;
+  e->stateBytes = (size_t)e->nPadded * CHUNKS * 16;
+  e->slabBytes = (size_t)max_found * KGX_ITEM_SIZE + 4;
+  if ((s = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", s);
+  if ((s = cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", s);
+  for (int i = 0; i < 2; i++) {
+    if ((s = cudaEventCreate(&e->evStart[i])) != cudaSuccess) return fail("cudaEventCreate", s);
+    if ((s = cudaEventCreateWithFlags(&e->evStop[i], cudaEventBlockingSync)) != cudaSuccess) return fail("cudaEventCreate", s);
+  }
+  if ((s = cudaMalloc(&e->state, e->stateBytes)) != cudaSuccess) return fail("cudaMalloc(state)", s);
+  for (int i = 0; i < 2; i++) {
+    if ((s = cudaMalloc(&e->slab[i], e->slabBytes)) != cudaSuccess) return fail("cudaMalloc(slab)", s);
+    if ((s = cudaMemsetAsync(e->slab[i], 0, 4, e->stream)) != cudaSuccess) return fail("cudaMemset(slab)", s);  // Check.cpp:526 collects before any launch
+  }
+  if ((s = cudaMalloc(&e->jtab, JT_WORDS * 4)) != cudaSuccess) return fail("cudaMalloc(jtab)", s);
+  if ((s = cudaHostAlloc(&e->slabPinned, e->slabBytes, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", s);
+  if ((s = cudaFuncSetAttribute(jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(smem)", s);
+  if ((s = cudaStreamSynchronize(e->stream)) != cudaSuccess) return fail("sync", s);
+  return e;
+}
+
+uint64_t kgx_num_kangaroos(kgx_engine* e) { return e->n; }
+uint64_t kgx_memory_bytes(kgx_engine* e) { return e->stateBytes + 2 * e->slabBytes + JT_WORDS * 4; }
+uint32_t kgx_max_found(kgx_engine* e) { return e->maxFound; }
+float kgx_last_launch_ms(kgx_engine* e) { return e->lastMs; }
+uint64_t kgx_kernel_launches(kgx_engine* e) { return e->launches; }
+int kgx_set_jumps_per_launch(kgx_engine* e, int n_run) {
+  if (n_run <= 0) { snprintf(e->err, sizeof e->err, "kgx_set_jumps_per_launch: n_run must be > 0"); return -1; }
+  e->nRun = n_run; return 0;
+}
+
+int kgx_set_params(kgx_engine* e, uint64_t dp_mask, const uint64_t* jd, const uint64_t* jpx, const uint64_t* jpy) {
+  CK(e, cudaSetDevice(e->dev));
+  u32 tab[JT_WORDS];
+  for (int j = 0; j < 32; j++) {
+    for (int w = 0; w < 8; w++) {
+      tab[w * 32 + j] = (u32)(jpx[4 * j + w / 2] >> (32 * (w & 1)));
+      tab[(8 + w) * 32 + j] = (u32)(jpy[4 * j + w / 2] >> (32 * (w & 1)));
+    }
+    for (int w = 0; w < 4; w++) tab[(16 + w) * 32 + j] = (u32)(jd[2 * j + w / 2] >> (32 * (w & 1)));
+  }
+  CK(e, cudaStreamSynchronize(e->stream));   // a running kernel may still read the old table
+  CK(e, cudaMemcpy(e->jtab, tab, sizeof tab, cudaMemcpyHostToDevice));
+  e->dpMask = dp_mask;
+  e->haveParams = true;
+  return 0;
+}
+
+static int ensure_staging(kgx_engine* e) {
+  if (e->stgX) return 0;
+  CK(e, cudaMalloc(&e->stgX, e->n * 32));
+  CK(e, cudaMalloc(&e->stgY, e->n * 32));
+  CK(e, cudaMalloc(&e->stgD, e->n * 16));
+  return 0;
+}
+static void free_staging(kgx_engine* e) {
+  cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
+  e->stgX = e->stgY = e->stgD = nullptr;
+}
+
+int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint64_t* d) {
+  CK(e, cudaSetDevice(e->dev));
+  if (ensure_staging(e)) return -1;
+  CK(e, cudaMemcpyAsync(e->stgX, px, e->n * 32, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->stgY, py, e->n * 32, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->stgD, d, e->n * 16, cudaMemcpyHostToDevice, e->stream));
+  u32 blocks = (u32)((e->nPadded + 255) / 256);
+  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  CK(e, cudaStreamSynchronize(e->stream));
+  free_staging(e);
+  return 0;
+}
+
+int kgx_download(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d) {
+  CK(e, cudaSetDevice(e->dev));
+  if (ensure_staging(e)) return -1;
+  u32 blocks = (u32)((e->n + 255) / 256);
+  unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n);   // stream order: after the in-flight launch
+  e->launches++;
+  CK(e, cudaGetLastError());
+  CK(e, cudaMemcpyAsync(px, e->stgX, e->n * 32, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(py, e->stgY, e->n * 32, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(d, e->stgD, e->n * 16, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  free_staging(e);
+  return 0;
+}
+
+int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t py[4], const uint64_t d[2]) {
+  CK(e, cudaSetDevice(e->dev));
+  if (kidx >= e->n) { snprintf(e->err, sizeof e->err, "kgx_patch: kidx out of range"); return -1; }
+  PatchArgs a;
+  memcpy(&a.c[0], px, 32); memcpy(&a.c[2], py, 32); memcpy(&a.c[4], d, 16);
+  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
+  e->launches++;
+  CK(e, cudaGetLastError());
+  // padding slots replicate kangaroo (s % n): keep them walking their stale copy -- harmless, their DPs are dropped.
+  return 0;
+}
+
+int kgx_launch_async(kgx_engine* e) {
+  CK(e, cudaSetDevice(e->dev));
+  if (!e->haveParams) { snprintf(e->err, sizeof e->err, "kgx_launch_async: kgx_set_params not called"); return -1; }
+  if (e->inflight) { snprintf(e->err, sizeof e->err, "kgx_launch_async: previous launch not collected"); return -1; }
+  int sidx = e->cur ^ 1;
+  LaunchParams p;
+  p.state = e->state; p.jtab = e->jtab; p.out = e->slab[sidx]; p.dpMask = e->dpMask; p.nKangaroos = e->n;
+  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun;
+  CK(e, cudaMemsetAsync(e->slab[sidx], 0, 4, e->stream));            // GPUEngine.cu:543
+  CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
+  u32 grid = (u32)(2 * e->sms);
+  if (grid > e->numTiles) grid = e->numTiles;
+  jump_kernel<<<grid, T, SMEM_BYTES, e->stream>>>(p);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  CK(e, cudaEventRecord(e->evStop[sidx], e->stream));
+  e->cur = sidx;
+  e->inflight = true;
+  return 0;
+}
+
+int kgx_collect(kgx_engine* e, kgx_item* items, uint32_t cap, uint32_t* n_items, uint32_t* n_found, int spin, int relaunch) {
+  CK(e, cudaSetDevice(e->dev));
+  *n_items = 0; *n_found = 0;
+  int sidx = e->cur;
+  if (e->inflight) {
+    if (spin) {
+      while (cudaEventQuery(e->evStop[sidx]) == cudaErrorNotReady) { }
+    } else {
+      CK(e, cudaEventSynchronize(e->evStop[sidx]));   // blocking-sync event: the host thread sleeps (GPUEngine.cu:620-629)
+    }
+    CK(e, cudaGetLastError());
+    CK(e, cudaEventElapsedTime(&e->lastMs, e->evStart[sidx], e->evStop[sidx]));
+    e->inflight = false;
+    e->done = sidx;
+  }
+  if (relaunch) { if (kgx_launch_async(e)) return -1; }   // second half of GPUEngine::Launch, issued BEFORE the readback
+  // read back slab `sidx` (the new launch writes the other slab)
+  // (on its own stream, so it does not queue behind the kernel just started)
+  CK(e, cudaMemcpyAsync(e->slabPinned, e->slab[sidx], 4, cudaMemcpyDeviceToHost, e->copyStream));
+  CK(e, cudaStreamSynchronize(e->copyStream));
+  u32 found = e->slabPinned[0];
+  *n_found = found;
+  u32 nrec = found > e->maxFound ? e->maxFound : found;
+  if (nrec > cap) nrec = cap;
+  if (nrec) {
+    CK(e, cudaMemcpyAsync(e->slabPinned + 1, e->slab[sidx] + 1, (size_t)nrec * KGX_ITEM_SIZE, cudaMemcpyDeviceToHost, e->copyStream));
+    CK(e, cudaStreamSynchronize(e->copyStream));
+    memcpy(items, e->slabPinned + 1, (size_t)nrec * KGX_ITEM_SIZE);
+  }
+  *n_items = nrec;
+  return 0;
+}
+
+int kgx_sync(kgx_engine* e) {
+  CK(e, cudaSetDevice(e->dev));
+  CK(e, cudaStreamSynchronize(e->stream));
+  if (e->inflight) {
+    CK(e, cudaEventElapsedTime(&e->lastMs, e->evStart[e->cur], e->evStop[e->cur]));
+    e->inflight = false; e->done = e->cur;
+  }
+  return 0;
+}
+
+void* kgx_dp_slab_device(kgx_engine* e) { return e->done >= 0 ? (void*)e->slab[e->done] : (void*)e->slab[e->cur]; }
+
+// ---- test / microbench hooks ----
+static char g_hook_err[256];
+#define CKH(call) do { cudaError_t _s = (call); if (_s != cudaSuccess) { snprintf(g_create_err, sizeof g_create_err, "%s: %s", #call, cudaGetErrorString(_s)); return -1; } } while (0)
+
+int kgx_test_field(int dev, int op, int n, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  (void)g_hook_err;
+  CKH(cudaSetDevice(dev));
+  u32 *da, *db, *dout;
+  CKH(cudaMalloc(&da, (size_t)n * 32)); CKH(cudaMalloc(&db, (size_t)n * 32)); CKH(cudaMalloc(&dout, (size_t)n * 32));
+  CKH(cudaMemcpy(da, a, (size_t)n * 32, cudaMemcpyHostToDevice));
+  CKH(cudaMemcpy(db, b, (size_t)n * 32, cudaMemcpyHostToDevice));
+  test_field_kernel<<<(n + 127) / 128, 128>>>(op, n, da, db, dout);
+  CKH(cudaGetLastError());
+  CKH(cudaMemcpy(out, dout, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return 0;
+}
+
+int kgx_bench_raw(int dev, int kind, int iters, float* ms, double* ops) {
+  CKH(cudaSetDevice(dev));
+  cudaDeviceProp prop; CKH(cudaGetDeviceProperties(&prop, dev));
+  u32* sink; CKH(cudaMalloc(&sink, 4));
+  cudaEvent_t a, b; CKH(cudaEventCreate(&a)); CKH(cudaEventCreate(&b));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  bench_raw_kernel<<<blocks, threads>>>(kind, iters / 8 + 1, sink);   // warm-up
+  CKH(cudaDeviceSynchronize());
+  CKH(cudaEventRecord(a));
+  bench_raw_kernel<<<blocks, threads>>>(kind, iters, sink);
+  CKH(cudaEventRecord(b));
+  CKH(cudaEventSynchronize(b));
+  CKH(cudaGetLastError());
+  CKH(cudaEventElapsedTime(ms, a, b));
+  double per_thread = kind == 0 ? 8.0 * iters : (kind == 3 ? 1.0 * iters : 2.0 * iters);
+  *ops = per_thread * (double)blocks * threads;
+  cudaFree(sink); cudaEventDestroy(a); cudaEventDestroy(b);
+  return 0;
+}
+
+}  // extern "C"
