@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- MJump/s of the B200 kangaroo jump engine (BASELINE.json metric) + roofline + CPU baseline.
+
+One "step" = one GPUEngine::Launch on the full herd: NB_RUN=64 jumps for every kangaroo of the default B200
+grid (2*148 x 128 threads x 128 = 4,849,664 kangaroos, the size the reference's GetGridSize picks,
+GPUEngine.cu:301-303), jump table of the in80 configuration (VC_CUDA8/in80.txt: 2^79.8 range -> rangePower 80,
+dp = 16), the reference's own throughput accounting `nbKangaroo * NB_RUN` per Launch (Kangaroo.cpp:575).
+
+  value : jumps / device time of exactly K launches (state resident in HBM, DP slabs left on the device)
+  e2e   : the same K launches through the reference-shaped host API (GPUEngine.Launch -> std::vector<ITEM>
+          equivalent): every step waits for the kernel, reads the DP records back to HOST memory and decodes
+          them, exactly what Kangaroo::SolveKeyGPU consumes.  The herd itself is resident by design of the
+          reference interface (SetKangaroos once, GPUEngine.cu:381-433), so h2d per step is 0 payload bytes.
+  roofline : integer-multiply bound: 416 IMAD.WIDE per jump (5 ModMult x 74 + ModSqr x 46) against
+          the MEASURED wide-IMAD issue rate of this box (scripts/ubench, profiles/), plus the HBM view.
+  cpu_baseline : the reference's SolveKeyCPU inner loop (oracle/_ref/libkref.so = unmodified SECPK1 code) on all
+          host cores for a bounded sample.
+
+`--impl reference` times that CPU implementation alone.  Under torchrun (N>1) one rank per GPU, independent
+herds (weak scaling), DP records gathered to rank 0 over NCCL every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB_RUN = 64
+ALGO_IMAD_PER_JUMP = 416          # SURVEY.md 8d / BASELINE.md 3
+ALGO_BYTES_PER_JUMP = 2.5         # 2 x 80 B per kangaroo per 64 jumps
+WIDE_IMAD_PER_CLK_SM = 32.0       # measured on B200 (scripts/ubench.cu, profiles/ubench_r1.txt): IMAD.WIDE.U32 issues at half rate
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(seconds_target):
+    """SolveKeyCPU inner loop through the reference's own Int/IntGroup code on all host cores."""
+    from oracle import kgo
+    cores = host_cores()
+    if os.path.exists(kgo.Reference.path):
+        be, kind = kgo.Reference(), "reference"
+    else:
+        be, kind = kgo.Oracle(), "port"
+    jumps, sec = be.bench_cpu(cores, 256, 80)                       # calibration: 256 jumps x 1024 kangaroos / thread
+    rate = jumps / sec
+    per_thread = max(256, int(seconds_target * rate / cores / 1024))
+    jumps, sec = be.bench_cpu(cores, per_thread, 80)
+    return dict(value=jumps / sec / 1e6, unit="MJump/s", cores=cores, kind=kind,
+                sample="%d threads x 1024 kangaroos x %d jumps (SolveKeyCPU inner loop, CPU_GRP_SIZE=1024, rangePower 80), %.1f s"
+                       % (cores, per_thread, sec)), sec
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.samples, self.reasons, self.stop_flag, self.max_mhz = dev, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(s))
+
+
+def load_in80_table():
+    """Jump table for rangePower 80 from the reference-generated fixture (tests/golden/jump_golden.json)."""
+    from tests.golden_util import load_cases
+    for c in load_cases():
+        if c["range_power"] == 80:
+            return c
+    raise RuntimeError("in80 fixture missing")
+
+
+def build_herd(eng, case, rank):
+    """Synthetic herd of valid walkers: the fixture's reference-generated start rows tiled over the grid, then
+    decorrelated ON THE DEVICE by giving every 128-row replica a different number of warm-up jumps."""
+    import numpy as np
+    from tests.golden_util import arrays
+    n = eng.nbKangaroo
+    sx, sy, sd = arrays(case["start"])
+    rows = sx.shape[0]
+    idx = (np.arange(n) + rank * 17) % rows
+    d = np.zeros((n, 2), dtype=np.uint64)
+    d[:, 0] = sd[idx, 0]; d[:, 1] = sd[idx, 1]
+    eng.SetKangaroosRaw(sx[idx], sy[idx], d)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", default="", help="x,y override (default 2*SMs,128)")
+    ap.add_argument("--dp", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        per_step_s = 4.0
+        base, _ = cpu_reference_run(per_step_s)
+        vals = []
+        for _ in range(warmup):
+            cpu_reference_run(1.0)
+        t0 = time.time()
+        for _ in range(steps):
+            r, _ = cpu_reference_run(per_step_s)
+            vals.append(r["value"])
+            if time.time() - t0 > 150:
+                break
+        v = sum(vals) / len(vals)
+        base["value"] = v
+        print(json.dumps(dict(impl="reference", metric="MJump/s (kangaroo jumps/sec)", value=v, unit="MJump/s", n_gpus=args.gpus,
+                              steps=len(vals), warmup=warmup, ms_per_step=per_step_s * 1e3, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="u32x8 (256-bit modular integer)", data="synthetic",
+                              config={"workload": "in80.txt-style: rangePower 80 jump table, SolveKeyCPU inner loop on all host cores",
+                                      "group": 1024}, cpu_baseline=base,
+                              e2e=dict(value=v, unit="MJump/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    import numpy as np
+    import torch
+    import kangaroo_b200
+    from kangaroo_b200 import GPUEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the jump engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    gx, gy = (int(v) for v in args.grid.split(",")) if args.grid else GPUEngine.GetGridSize(local_rank, 0, 0)
+    case = load_in80_table()
+    max_found = 1 << 17                                            # Kangaroo.cpp:523 (65536*2)
+    eng = GPUEngine(gx, gy, local_rank, max_found)
+    n = eng.nbKangaroo
+    dp_mask = (~((1 << (64 - args.dp)) - 1)) & 0xFFFFFFFFFFFFFFFF if args.dp else 0
+    eng.SetParams(dp_mask, *case["table"])
+    eng.SetWildOffset(0)
+    build_herd(eng, case, rank)
+
+    from kangaroo_b200.dist import DPGather
+    gather = DPGather(eng, dist, rank, world, torch) if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: K launches, DP slabs stay on the device -----------------------------------
+    lib = kangaroo_b200.load_library()
+    import ctypes
+    nI, nF = ctypes.c_uint32(0), ctypes.c_uint32(0)
+
+    def device_step():
+        # wait for the launch in flight, start the next one; cap=0 -> no host readback of records
+        rc = lib.kgx_collect(eng._h, eng._items, 0, ctypes.byref(nI), ctypes.byref(nF), 0, 1)
+        assert rc == 0, lib.kgx_last_error(eng._h)
+        if gather is not None:
+            gather.step(int(nF.value))
+        return eng.last_launch_ms(), int(nF.value)
+
+    eng.callKernel()
+    for _ in range(max(warmup, 3)):
+        device_step()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = eng.kernel_launches()
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms, found = [], 0
+    for _ in range(steps):
+        ms, nf = device_step()
+        kernel_ms.append(ms); found += nf
+    eng.sync()
+    barrier()
+    wall = time.perf_counter() - t0
+    gpu_launches = eng.kernel_launches() - launches0
+    # the K timed launches are exactly the K kernels completed inside the region: (K-1) collected + the one synced
+    kernel_ms = kernel_ms[1:] + [eng.last_launch_ms()]
+    dev_s = sum(kernel_ms) / 1e3
+
+    # ---- end-to-end leg through the reference-shaped API (host ITEM lists) ------------------------------
+    eng.callKernel()
+    for _ in range(2):
+        eng.Launch()
+    barrier()
+    t1 = time.perf_counter()
+    d2h = 0
+    for _ in range(steps):
+        items = eng.Launch()
+        d2h += 4 + len(items) * 56
+        if gather is not None:
+            gather.step(len(items))
+    eng.sync()
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    t = torch.tensor([dev_s, wall, e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, wall, e2e_s = (float(v) for v in t.tolist())
+    total_jumps = float(n) * NB_RUN * steps * world
+    value = total_jumps / wall / 1e6                 # whole job, wall clock between barriers (max over ranks)
+    kernel_value = float(n) * NB_RUN * steps / dev_s / 1e6
+    e2e_value = total_jumps / e2e_s / 1e6
+
+    if rank == 0:
+        clocks = sampler.result()
+        mhz = clocks["sm_mhz"] or 1965.0
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        imad_peak = sms * WIDE_IMAD_PER_CLK_SM * mhz * 1e6
+        achieved = kernel_value * 1e6 * ALGO_IMAD_PER_JUMP
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback"
+        hbm_ach = kernel_value * 1e6 * ALGO_BYTES_PER_JUMP / 1e9
+        out = dict(
+            metric="MJump/s (kangaroo jumps/sec)", value=value, unit="MJump/s", n_gpus=world, steps=steps, warmup=max(warmup, 3),
+            ms_per_step=wall / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="u32x8 (256-bit modular integer)", data="synthetic",
+            config={"workload": "in80.txt: rangePower 80 jump table, dp=%d, grid %dx%d -> %d kangaroos/GPU x NB_RUN=64 jumps per step"
+                                % (args.dp, gx, gy, n),
+                    "state_bytes_per_gpu": n * 80, "l2_note": "388 MB of kangaroo state per GPU > 126 MB L2; every step streams all of it",
+                    "dp_found_per_step": found / max(steps, 1)},
+            kernel_only={"value": kernel_value, "unit": "MJump/s/GPU", "ms_per_launch": dev_s / steps * 1e3,
+                         "how": "CUDA events on the engine stream around each jump_kernel launch"},
+            e2e={"value": e2e_value, "unit": "MJump/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / max(steps, 1),
+                 "how": "GPUEngine.Launch loop: wait, DP records -> pinned host -> ITEM list, relaunch (Kangaroo.cpp:572-575)"},
+            roofline={"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s (32x32->64 multiply-adds)",
+                      "frac": achieved / imad_peak, "traffic": None,
+                      "algorithmic_imad_per_jump": ALGO_IMAD_PER_JUMP,
+                      "peak_how": "%d SMs x %.0f IMAD.WIDE/clk/SM (measured, scripts/ubench) x %.0f MHz (median SM clock under load)"
+                                  % (sms, WIDE_IMAD_PER_CLK_SM, mhz),
+                      "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                              "peak_source": hbm_src, "algorithmic_bytes_per_jump": ALGO_BYTES_PER_JUMP}},
+            gpu_launches=int(gpu_launches), clocks=clocks)
+        if not args.no_cpu_baseline and world >= 1:
+            base, _ = cpu_reference_run(12.0)
+            out["cpu_baseline"] = base
+            out["speedup_vs_cpu_e2e"] = e2e_value / base["value"]
+        print(json.dumps(out))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
