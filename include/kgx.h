@@ -80,6 +80,10 @@ int      kgx_set_jumps_per_launch(kgx_engine* e, int n_run);
 /* Number of kernels this engine has launched so far (jump + pack/unpack/patch), for bench.py's gpu_launches. */
 uint64_t kgx_kernel_launches(kgx_engine* e);
 
+/* Debug (KGX_PROF=1 in the environment at kgx_create): phase cycle counters summed over warp 0 of every CTA:
+ * out = {serial section, modular inverse alone, parallel phase, tile-steps}; resets them. -1 when disabled. */
+int      kgx_debug_prof(kgx_engine* e, uint64_t out[4]);
+
 /* --- device-side unit-test / microbenchmark hooks (kgx_field.cuh, kgx_modinv.h) --- */
 /* op: 0 = mul, 1 = sqr, 2 = sub, 3 = inv.  a, b, out: n x 4 limbs on the HOST. */
 int kgx_test_field(int dev, int op, int n, const uint64_t* a, const uint64_t* b, uint64_t* out);

@@ -41,6 +41,7 @@ _SIGS = {
     "kgx_last_launch_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "kgx_set_jumps_per_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kgx_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "kgx_debug_prof": (ctypes.c_int, [ctypes.c_void_p, _u64p]),
     "kgx_test_field": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p]),
     "kgx_bench_raw": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                      ctypes.POINTER(ctypes.c_double)]),

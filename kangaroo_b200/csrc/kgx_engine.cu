@@ -19,10 +19,13 @@ static char g_create_err[256] = "";
 
 struct kgx_engine {
   int dev = 0, groups = 0, tpg = 0, sms = 0;
+  int T = 0, K = 0, cfg = 0, ctasPerSM = 0, smemBytes = 0;   // tile geometry (kgx_kernel.cuh Cfg<T,K>)
   u64 n = 0, nPadded = 0;
   u32 numTiles = 0, maxFound = 0;
   int nRun = KGX_NB_RUN;
   uint4* state = nullptr;
+  uint4* pre = nullptr;      // streaming mode: prefix-product scratch
+  bool streamMode = false;
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
   u32* slabPinned = nullptr;
   u32* jtab = nullptr;
@@ -34,6 +37,7 @@ struct kgx_engine {
   cudaStream_t stream = nullptr, copyStream = nullptr;
   cudaEvent_t evStart[2] = {nullptr, nullptr}, evStop[2] = {nullptr, nullptr};
   float lastMs = 0.f;
+  unsigned long long* prof = nullptr;   // KGX_PROF=1: phase cycle counters
   u64 launches = 0;
   size_t slabBytes = 0, stateBytes = 0;
   char err[256] = "";
@@ -47,6 +51,21 @@ struct kgx_engine {
       return -1;                                                                               \
     }                                                                                          \
   } while (0)
+
+// Tile geometries compiled in.  The default was picked by the sweep recorded in profiles/ (KGX_CFG="T,K" overrides).
+struct CfgEntry { int T, K, smem, ctas; void (*kern)(LaunchParams); };
+#define KGX_CFG_ENTRY(T_, K_) { T_, K_, Cfg<T_, K_>::SMEM_BYTES, Cfg<T_, K_>::CTAS_PER_SM, jump_kernel<T_, K_> }
+static const CfgEntry g_cfgs[] = {
+  KGX_CFG_ENTRY(128, 7), KGX_CFG_ENTRY(128, 4), KGX_CFG_ENTRY(128, 5), KGX_CFG_ENTRY(64, 7), KGX_CFG_ENTRY(64, 5),
+  KGX_CFG_ENTRY(64, 6), KGX_CFG_ENTRY(64, 4), KGX_CFG_ENTRY(96, 6), KGX_CFG_ENTRY(256, 3), KGX_CFG_ENTRY(32, 8), KGX_CFG_ENTRY(32, 12),
+};
+static const int g_ncfg = sizeof(g_cfgs) / sizeof(g_cfgs[0]);
+#ifndef KGX_DEFAULT_CFG
+#define KGX_DEFAULT_CFG 0
+#endif
+#ifndef KGX_DEFAULT_STREAM
+#define KGX_DEFAULT_STREAM 0
+#endif
 
 extern "C" {
 
@@ -81,7 +100,7 @@ void kgx_destroy(kgx_engine* e) {
   if (!e) return;
   cudaSetDevice(e->dev);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->state); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
+  cudaFree(e->state); cudaFree(e->pre); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
   cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
   if (e->slabPinned) cudaFreeHost(e->slabPinned);
   for (int i = 0; i < 2; i++) { if (e->evStart[i]) cudaEventDestroy(e->evStart[i]); if (e->evStop[i]) cudaEventDestroy(e->evStop[i]); }
@@ -112,6 +131,24 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
   if ((s = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return fail("cudaGetDeviceProperties", s);
   e->dev = dev; e->groups = groups; e->tpg = threads_per_group; e->sms = prop.multiProcessorCount;
   e->n = (u64)groups * (u64)threads_per_group * KGX_GPU_GRP_SIZE;
+  e->cfg = KGX_DEFAULT_CFG;
+  if (const char* env = getenv("KGX_CFG")) {
+    int t = 0, k = 0, found = -1;
+    if (sscanf(env, "%d,%d", &t, &k) == 2)
+      for (int i = 0; i < g_ncfg; i++) if (g_cfgs[i].T == t && g_cfgs[i].K == k) found = i;
+    if (found < 0) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_CFG=%s is not a compiled tile geometry", env); delete e; return nullptr; }
+    e->cfg = found;
+  }
+  e->T = g_cfgs[e->cfg].T; e->K = g_cfgs[e->cfg].K; e->smemBytes = g_cfgs[e->cfg].smem; e->ctasPerSM = g_cfgs[e->cfg].ctas;
+  {
+    const char* mode = getenv("KGX_MODE");
+    e->streamMode = mode ? (strcmp(mode, "stream") == 0) : (KGX_DEFAULT_STREAM != 0);
+    if (mode && strcmp(mode, "stream") && strcmp(mode, "resident")) {
+      snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream or resident"); delete e; return nullptr;
+    }
+    if (e->streamMode) { e->T = 128; e->K = 128; e->smemBytes = 0; e->ctasPerSM = 2; }
+  }
+  const u64 TILE = (u64)e->T * e->K;
   e->numTiles = (u32)((e->n + TILE - 1) / TILE);
   e->nPadded = (u64)e->numTiles * TILE;
   e->maxFound = max_found;
@@ -124,23 +161,37 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
     if ((s = cudaEventCreateWithFlags(&e->evStop[i], cudaEventBlockingSync)) != cudaSuccess) return fail("cudaEventCreate", s);
   }
   if ((s = cudaMalloc(&e->state, e->stateBytes)) != cudaSuccess) return fail("cudaMalloc(state)", s);
+  if (e->streamMode && (s = cudaMalloc(&e->pre, (size_t)e->nPadded * 32)) != cudaSuccess) return fail("cudaMalloc(pre)", s);
   for (int i = 0; i < 2; i++) {
     if ((s = cudaMalloc(&e->slab[i], e->slabBytes)) != cudaSuccess) return fail("cudaMalloc(slab)", s);
     if ((s = cudaMemsetAsync(e->slab[i], 0, 4, e->stream)) != cudaSuccess) return fail("cudaMemset(slab)", s);  // Check.cpp:526 collects before any launch
   }
   if ((s = cudaMalloc(&e->jtab, JT_WORDS * 4)) != cudaSuccess) return fail("cudaMalloc(jtab)", s);
+  if (getenv("KGX_PROF")) {
+    if ((s = cudaMalloc(&e->prof, 64)) != cudaSuccess) return fail("cudaMalloc(prof)", s);
+    cudaMemset(e->prof, 0, 64);
+  }
   if ((s = cudaHostAlloc(&e->slabPinned, e->slabBytes, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", s);
-  if ((s = cudaFuncSetAttribute(jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
+  if (!e->streamMode &&
+      (s = cudaFuncSetAttribute(g_cfgs[e->cfg].kern, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smemBytes)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(smem)", s);
   if ((s = cudaStreamSynchronize(e->stream)) != cudaSuccess) return fail("sync", s);
   return e;
 }
 
 uint64_t kgx_num_kangaroos(kgx_engine* e) { return e->n; }
-uint64_t kgx_memory_bytes(kgx_engine* e) { return e->stateBytes + 2 * e->slabBytes + JT_WORDS * 4; }
+uint64_t kgx_memory_bytes(kgx_engine* e) { return e->stateBytes + (e->pre ? e->nPadded * 32 : 0) + 2 * e->slabBytes + JT_WORDS * 4; }
 uint32_t kgx_max_found(kgx_engine* e) { return e->maxFound; }
 float kgx_last_launch_ms(kgx_engine* e) { return e->lastMs; }
 uint64_t kgx_kernel_launches(kgx_engine* e) { return e->launches; }
+// debug: read and reset the phase counters (KGX_PROF=1): serial, modinv, parallel cycles, tile-steps
+int kgx_debug_prof(kgx_engine* e, uint64_t out[4]) {
+  if (!e->prof) return -1;
+  cudaStreamSynchronize(e->stream);
+  cudaMemcpy(out, e->prof, 32, cudaMemcpyDeviceToHost);
+  cudaMemset(e->prof, 0, 64);
+  return 0;
+}
 int kgx_set_jumps_per_launch(kgx_engine* e, int n_run) {
   if (n_run <= 0) { snprintf(e->err, sizeof e->err, "kgx_set_jumps_per_launch: n_run must be > 0"); return -1; }
   e->nRun = n_run; return 0;
@@ -182,7 +233,7 @@ int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint
   CK(e, cudaMemcpyAsync(e->stgY, py, e->n * 32, cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaMemcpyAsync(e->stgD, d, e->n * 16, cudaMemcpyHostToDevice, e->stream));
   u32 blocks = (u32)((e->nPadded + 255) / 256);
-  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded);
+  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K);
   e->launches++;
   CK(e, cudaGetLastError());
   CK(e, cudaStreamSynchronize(e->stream));
@@ -194,7 +245,7 @@ int kgx_download(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d) {
   CK(e, cudaSetDevice(e->dev));
   if (ensure_staging(e)) return -1;
   u32 blocks = (u32)((e->n + 255) / 256);
-  unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n);   // stream order: after the in-flight launch
+  unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->T, e->K);   // stream order: after the in-flight launch
   e->launches++;
   CK(e, cudaGetLastError());
   CK(e, cudaMemcpyAsync(px, e->stgX, e->n * 32, cudaMemcpyDeviceToHost, e->stream));
@@ -210,7 +261,7 @@ int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t
   if (kidx >= e->n) { snprintf(e->err, sizeof e->err, "kgx_patch: kidx out of range"); return -1; }
   PatchArgs a;
   memcpy(&a.c[0], px, 32); memcpy(&a.c[2], py, 32); memcpy(&a.c[4], d, 16);
-  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
+  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a, e->T, e->K);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
   e->launches++;
   CK(e, cudaGetLastError());
   // padding slots replicate kangaroo (s % n): keep them walking their stale copy -- harmless, their DPs are dropped.
@@ -224,12 +275,13 @@ int kgx_launch_async(kgx_engine* e) {
   int sidx = e->cur ^ 1;
   LaunchParams p;
   p.state = e->state; p.jtab = e->jtab; p.out = e->slab[sidx]; p.dpMask = e->dpMask; p.nKangaroos = e->n;
-  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun;
+  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre;
   CK(e, cudaMemsetAsync(e->slab[sidx], 0, 4, e->stream));            // GPUEngine.cu:543
   CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
-  u32 grid = (u32)(2 * e->sms);
+  u32 grid = (u32)(e->ctasPerSM * e->sms);
   if (grid > e->numTiles) grid = e->numTiles;
-  jump_kernel<<<grid, T, SMEM_BYTES, e->stream>>>(p);
+  if (e->streamMode) stream_kernel<128, 128><<<grid, 128, 0, e->stream>>>(p);
+  else g_cfgs[e->cfg].kern<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   e->launches++;
   CK(e, cudaGetLastError());
   CK(e, cudaEventRecord(e->evStop[sidx], e->stream));

@@ -150,10 +150,112 @@ __device__ __forceinline__ void fe_mul(u32* r, const u32* a, const u32* b) {
   kgx_fold(r, w);
 }
 
-// a^2: 28 cross products (doubled) + 8 squares.
+// carry chains of 1..3 column pairs (kgx_mad_row is the 4-pair form): acc[0..2n-1] += {a...} * b, carry into acc[2n]
+__device__ __forceinline__ void kgx_mad_c1(u32* acc, u32 b, u32 a0) {
+  asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32       %2, %2, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(a0), "r"(b));
+}
+__device__ __forceinline__ void kgx_mad_c2(u32* acc, u32 b, u32 a0, u32 a1) {
+  asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32       %4, %4, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(a0), "r"(a1), "r"(b));
+}
+__device__ __forceinline__ void kgx_mad_c3(u32* acc, u32 b, u32 a0, u32 a1, u32 a2) {
+  asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+      "addc.u32       %6, %6, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+}
+
+// a^2 as 28 cross products (computed once, doubled) + 8 squares: 36 IMAD.WIDE instead of 64.
+// Same exact 512-bit value as a*a, hence the same folded result (GPUMath.h:909-1019 / IntMod.cpp:1030-1234).
+__device__ __forceinline__ void kgx_sqr512(u32* w, const u32* a) {
+  u32 E[16], O[15];
+#pragma unroll
+  for (int i = 0; i < 16; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 15; i++) O[i] = 0;
+  // E[i] sits at word i, O[i] at word i+1; product a_i*a_j lands at word i+j
+  kgx_mad_row(O + 0, a[1], a[3], a[5], a[7], a[0]);   // 0x{1,3,5,7} -> words 1,3,5,7
+  kgx_mad_c3(E + 2, a[0], a[2], a[4], a[6]);          // 0x{2,4,6}   -> words 2,4,6
+  kgx_mad_c3(O + 2, a[1], a[2], a[4], a[6]);          // 1x{2,4,6}   -> words 3,5,7
+  kgx_mad_c3(E + 4, a[1], a[3], a[5], a[7]);          // 1x{3,5,7}   -> words 4,6,8
+  kgx_mad_c3(O + 4, a[2], a[3], a[5], a[7]);          // 2x{3,5,7}   -> words 5,7,9
+  kgx_mad_c2(E + 6, a[2], a[4], a[6]);                // 2x{4,6}     -> words 6,8
+  kgx_mad_c2(O + 6, a[3], a[4], a[6]);                // 3x{4,6}     -> words 7,9
+  kgx_mad_c2(E + 8, a[3], a[5], a[7]);                // 3x{5,7}     -> words 8,10
+  kgx_mad_c2(O + 8, a[4], a[5], a[7]);                // 4x{5,7}     -> words 9,11
+  kgx_mad_c1(E + 10, a[4], a[6]);                     // 4x6         -> word 10
+  kgx_mad_c1(O + 10, a[5], a[6]);                     // 5x6         -> word 11
+  kgx_mad_c1(E + 12, a[5], a[7]);                     // 5x7         -> word 12
+  kgx_mad_c1(O + 12, a[6], a[7]);                     // 6x7         -> word 13
+  // C = E + (O << 32), words 1..15 (word 0 is zero)
+  u32 c[16];
+  c[0] = 0;
+  asm("add.cc.u32  %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32    %14, %29, %44;"
+      : "=&r"(c[1]), "=&r"(c[2]), "=&r"(c[3]), "=&r"(c[4]), "=&r"(c[5]), "=&r"(c[6]), "=&r"(c[7]), "=&r"(c[8]),
+        "=&r"(c[9]), "=&r"(c[10]), "=&r"(c[11]), "=&r"(c[12]), "=&r"(c[13]), "=&r"(c[14]), "=&r"(c[15])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+        "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+        "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+  // 2C by funnel shifts (no carry chain)
+  u32 c2[16];
+  c2[0] = 0;
+#pragma unroll
+  for (int i = 15; i >= 1; i--) c2[i] = __funnelshift_l(c[i - 1], c[i], 1);
+  // + squares a_i^2 at words (2i, 2i+1)
+  asm("mad.lo.cc.u32  %0, %16, %16, %24;\n\t"
+      "madc.hi.cc.u32 %1, %16, %16, %25;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %26;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %27;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %28;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %29;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %30;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %31;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %32;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %33;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %34;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %35;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %36;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %37;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %38;\n\t"
+      "madc.hi.u32    %15, %23, %23, %39;"
+      : "=&r"(w[0]), "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]),
+        "=&r"(w[8]), "=&r"(w[9]), "=&r"(w[10]), "=&r"(w[11]), "=&r"(w[12]), "=&r"(w[13]), "=&r"(w[14]), "=&r"(w[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(c2[0]), "r"(c2[1]), "r"(c2[2]), "r"(c2[3]), "r"(c2[4]), "r"(c2[5]), "r"(c2[6]), "r"(c2[7]),
+        "r"(c2[8]), "r"(c2[9]), "r"(c2[10]), "r"(c2[11]), "r"(c2[12]), "r"(c2[13]), "r"(c2[14]), "r"(c2[15]));
+}
+
 __device__ __forceinline__ void fe_sqr(u32* r, const u32* a) {
-  // TODO(perf): dedicated squaring (36 IMAD.WIDE instead of 64)
-  fe_mul(r, a, a);
+  u32 w[16];
+  kgx_sqr512(w, a);
+  kgx_fold(r, w);
 }
 
 // r = a - b (mod 2^256), + p if borrow.   GPUMath.h:476-494 semantics.

@@ -22,20 +22,23 @@
 
 namespace kgx {
 
-constexpr int T = 128;            // threads per CTA
-constexpr int K = 7;              // kangaroos per thread
-constexpr int TILE = T * K;       // kangaroos per tile
 constexpr int CHUNKS = 5;         // 16-byte chunks per kangaroo in HBM: x0 x1 y0 y1 d
 constexpr int JT_WORDS = 20 * 32; // jump table: jpx[8][32] jpy[8][32] jd[4][32], word-major (bank = jump index)
 
-// shared memory carve-up (in uint4 units)
-constexpr int S_X = 0;
-constexpr int S_Y = S_X + K * 2 * T;
-constexpr int S_P = S_Y + K * 2 * T;
-constexpr int S_D = S_P + K * 2 * T;
-constexpr int S_TOT = S_D + K * T;
-constexpr int S_JT = S_TOT + 2 * T;                         // u32 view starts here
-constexpr int SMEM_BYTES = S_JT * 16 + JT_WORDS * 4;        // 107,008 B -> 2 CTAs / SM
+// Tile geometry: T threads per CTA (W = T/32 warps), K kangaroos per thread.  Shared memory (uint4 units):
+//   X[K][2][T] Y[K][2][T] P[K][2][T] D[K][T] TOT[2][T] then the jump table (u32 view).
+template <int T_, int K_>
+struct Cfg {
+  static constexpr int T = T_, K = K_, W = T_ / 32, TILE = T_ * K_;
+  static constexpr int S_X = 0;
+  static constexpr int S_Y = S_X + K * 2 * T;
+  static constexpr int S_P = S_Y + K * 2 * T;
+  static constexpr int S_D = S_P + K * 2 * T;
+  static constexpr int S_TOT = S_D + K * T;
+  static constexpr int S_JT = S_TOT + 2 * T;
+  static constexpr int SMEM_BYTES = S_JT * 16 + JT_WORDS * 4;
+  static constexpr int CTAS_PER_SM = (227 * 1024) / (SMEM_BYTES + 1024);
+};
 
 struct LaunchParams {
   uint4* state;          // [numTiles][K][CHUNKS][T]
@@ -46,6 +49,8 @@ struct LaunchParams {
   u32 numTiles;
   u32 maxFound;
   int nRun;
+  uint4* pre;            // streaming kernel only: prefix-product scratch [numTiles][G][2][T]
+  unsigned long long* prof;   // optional: [0]=sum serial cycles, [1]=sum modinv cycles, [2]=sum parallel cycles, [3]=tile-steps (warp 0 of every CTA)
 };
 
 __device__ __forceinline__ void lds_fe(u32* r, const uint4* base, int idx0, int idx1) {
@@ -65,27 +70,22 @@ __device__ __forceinline__ void shfl_xor_fe(u32* r, const u32* a, int mask) {
   for (int w = 0; w < 8; w++) r[w] = __shfl_xor_sync(0xffffffffu, a[w], mask);
 }
 
-// u32[8] <-> u64[4] for the inverse
-__device__ __forceinline__ void fe_inv(u32* r, const u32* a) {
-  uint64_t in[4], out[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) in[i] = (uint64_t)a[2 * i] | ((uint64_t)a[2 * i + 1] << 32);
-  modinv256(out, in);
-#pragma unroll
-  for (int i = 0; i < 4; i++) { r[2 * i] = (u32)out[i]; r[2 * i + 1] = (u32)(out[i] >> 32); }
-}
+__device__ __forceinline__ void fe_inv(u32* r, const u32* a) { modinv256(r, a); }
 
-// Warp 0 only: turn the 128 per-thread products in sTot into their 128 inverses (in place).
-__device__ __noinline__ void tile_inverse(uint4* sTot, int lane) {
-  u32 t0[8], t1[8], t2[8], t3[8], c1[8], c2[8], v[8];
-  lds_fe(t0, sTot, lane, T + lane);
-  lds_fe(t1, sTot, 32 + lane, T + 32 + lane);
-  lds_fe(t2, sTot, 64 + lane, T + 64 + lane);
-  lds_fe(t3, sTot, 96 + lane, T + 96 + lane);
-  fe_mul(c1, t0, t1);
-  fe_mul(c2, c1, t2);
-  fe_mul(v, c2, t3);
-  // XOR butterfly: after level k every lane holds the product of its 2^(k+1)-lane block; keep the siblings.
+// Warp 0 only: turn the T per-thread products in sTot into their T inverses (in place).
+// lane l chains the totals of threads {l, l+32, ...} (one per warp: conflict-free), the 32 lane products are
+// multiplied by an XOR butterfly (every lane ends with the tile product and keeps the 5 sibling factors),
+// one warp-uniform inverse, then the same tree is walked back.
+template <int T, int W>
+__device__ __noinline__ void tile_inverse(uint4* sTot, int lane, unsigned long long* prof) {
+  u32 tw[W][8], c[W][8];     // c[w] = tw[0]*...*tw[w]
+#pragma unroll
+  for (int w = 0; w < W; w++) lds_fe(tw[w], sTot, 32 * w + lane, T + 32 * w + lane);
+  fe_copy(c[0], tw[0]);
+#pragma unroll
+  for (int w = 1; w < W; w++) fe_mul(c[w], c[w - 1], tw[w]);
+  u32 v[8];
+  fe_copy(v, c[W - 1]);
   u32 sib[5][8];
 #pragma unroll
   for (int l = 0; l < 5; l++) {
@@ -93,30 +93,32 @@ __device__ __noinline__ void tile_inverse(uint4* sTot, int lane) {
     fe_mul(v, v, sib[l]);
   }
   u32 inv[8];
+  long long tq0 = prof ? clock64() : 0;
   fe_inv(inv, v);                 // identical in all 32 lanes
+  if (prof && lane == 0) atomicAdd(prof + 1, (unsigned long long)(clock64() - tq0));
 #pragma unroll
-  for (int l = 4; l >= 0; l--) fe_mul(inv, inv, sib[l]);   // -> inverse of this lane's c3 = t0*t1*t2*t3
-  u32 o[8];
-  fe_mul(o, inv, c2);             // 1/t3
-  sts_fe(sTot, 96 + lane, T + 96 + lane, o);
-  fe_mul(inv, inv, t3);           // 1/(t0 t1 t2)
-  fe_mul(o, inv, c1);             // 1/t2
-  sts_fe(sTot, 64 + lane, T + 64 + lane, o);
-  fe_mul(inv, inv, t2);           // 1/(t0 t1)
-  fe_mul(o, inv, t0);             // 1/t1
-  sts_fe(sTot, 32 + lane, T + 32 + lane, o);
-  fe_mul(o, inv, t1);             // 1/t0
-  sts_fe(sTot, lane, T + lane, o);
+  for (int l = 4; l >= 0; l--) fe_mul(inv, inv, sib[l]);   // -> 1 / c[W-1] of this lane
+#pragma unroll
+  for (int w = W - 1; w >= 1; w--) {
+    u32 o[8];
+    fe_mul(o, inv, c[w - 1]);     // 1 / tw[w]
+    sts_fe(sTot, 32 * w + lane, T + 32 * w + lane, o);
+    fe_mul(inv, inv, tw[w]);      // 1 / c[w-1]
+  }
+  sts_fe(sTot, lane, T + lane, inv);
 }
 
-__global__ void __launch_bounds__(T, 2) jump_kernel(LaunchParams p) {
+template <int T, int K>
+__global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchParams p) {
+  using C = Cfg<T, K>;
+  constexpr int TILE = C::TILE;
   extern __shared__ uint4 smem[];
-  uint4* sX = smem + S_X;
-  uint4* sY = smem + S_Y;
-  uint4* sP = smem + S_P;
-  uint4* sD = smem + S_D;
-  uint4* sTot = smem + S_TOT;
-  u32* sJ = reinterpret_cast<u32*>(smem + S_JT);
+  uint4* sX = smem + C::S_X;
+  uint4* sY = smem + C::S_Y;
+  uint4* sP = smem + C::S_P;
+  uint4* sD = smem + C::S_D;
+  uint4* sTot = smem + C::S_TOT;
+  u32* sJ = reinterpret_cast<u32*>(smem + C::S_JT);
   const u32* jpx = sJ;
   const u32* jpy = sJ + 8 * 32;
   const u32* jd = sJ + 16 * 32;
@@ -158,11 +160,17 @@ __global__ void __launch_bounds__(T, 2) jump_kernel(LaunchParams p) {
       sts_fe(sTot, t, T + t, P);
     }
     int backward = 1;   // the pass after a forward accumulation consumes in reverse order
+    long long tp0 = 0;
 
     for (int run = 0; run < p.nRun; run++) {
+      long long tp1 = (p.prof && t == 0) ? clock64() : 0;
+      if (p.prof && t == 0 && run > 0) atomicAdd(p.prof + 2, (unsigned long long)(tp1 - tp0));
       __syncthreads();
-      if (t < 32) tile_inverse(sTot, lane);
+      long long ts0 = (p.prof && t == 0) ? clock64() : 0;
+      if (t < 32) tile_inverse<T, C::W>(sTot, lane, p.prof);
+      if (p.prof && t == 0) { atomicAdd(p.prof + 0, (unsigned long long)(clock64() - ts0)); atomicAdd(p.prof + 3, 1ull); }
       __syncthreads();
+      tp0 = (p.prof && t == 0) ? clock64() : 0;
       u32 I[8];
       lds_fe(I, sTot, t, T + t);
       const bool last = (run == p.nRun - 1);
@@ -236,10 +244,131 @@ __global__ void __launch_bounds__(T, 2) jump_kernel(LaunchParams p) {
   }
 }
 
+// =====================================================================================================
+// Streaming variant: every THREAD owns a private Montgomery group of G kangaroos that live in HBM
+// ([tile][g][chunk][t], 16-byte chunks, lanes contiguous -> every warp access is one 512-byte line set).
+// No barriers, no cross-thread traffic: a thread inverts its own group product (lanes diverge inside the
+// variable-time safegcd, other warps fill the pipes meanwhile) and then makes ONE fused pass over its G
+// kangaroos per jump: read prefix/x/y/d (112 B), write x'/y'/d'/next prefix (112 B), software-prefetching the
+// next kangaroo while the current one is in the multiplier.  HBM traffic 224 B/jump instead of 2.5, but no
+// serial section at all; selected with KGX_MODE=stream (see DESIGN.md for the measured trade-off).
+// =====================================================================================================
+struct KangLoad { uint4 p0, p1, x0, x1, y0, y1, d; };
+
+template <int T>
+__device__ __forceinline__ void stream_load(KangLoad& k, const uint4* st, const uint4* pr, int g) {
+  k.p0 = pr[(g * 2 + 0) * T]; k.p1 = pr[(g * 2 + 1) * T];
+  k.x0 = st[(g * CHUNKS + 0) * T]; k.x1 = st[(g * CHUNKS + 1) * T];
+  k.y0 = st[(g * CHUNKS + 2) * T]; k.y1 = st[(g * CHUNKS + 3) * T];
+  k.d = st[(g * CHUNKS + 4) * T];
+}
+__device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) {
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+
+template <int T, int G>
+__global__ void __launch_bounds__(T, 2) stream_kernel(LaunchParams p) {
+  __shared__ u32 sJ[JT_WORDS];
+  const u32* jpx = sJ;
+  const u32* jpy = sJ + 8 * 32;
+  const u32* jd = sJ + 16 * 32;
+  const int t = threadIdx.x;
+  const u32 mlo = (u32)p.dpMask, mhi = (u32)(p.dpMask >> 32);
+  for (int i = t; i < JT_WORDS; i += T) sJ[i] = p.jtab[i];
+  __syncthreads();
+
+  for (u32 tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+    uint4* st = p.state + (size_t)tile * (G * CHUNKS * T) + t;
+    uint4* pr = p.pre + (size_t)tile * (G * 2 * T) + t;
+    u32 P[8];
+    {   // prologue: forward chain, pr[g] = product of the dx before g
+      u32 x[8], jx[8], dx[8];
+#pragma unroll 1
+      for (int g = 0; g < G; g++) {
+        unpack8(x, st[(g * CHUNKS + 0) * T], st[(g * CHUNKS + 1) * T]);
+        lds_jp(jx, jpx, x[0] & 31u);
+        fe_sub(dx, x, jx);
+        if (g == 0) {
+          pr[0] = make_uint4(1, 0, 0, 0); pr[T] = make_uint4(0, 0, 0, 0);
+          fe_copy(P, dx);
+        } else {
+          pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
+          fe_mul(P, P, dx);
+        }
+      }
+    }
+    int backward = 1;
+    for (int run = 0; run < p.nRun; run++) {
+      u32 I[8];
+      fe_inv(I, P);                              // this thread's own group: 1 / (dx_0 ... dx_{G-1})
+      const bool last = (run == p.nRun - 1);
+      KangLoad cur, nxt;
+      stream_load<T>(cur, st, pr, backward ? (G - 1) : 0);
+#pragma unroll 1
+      for (int i = 0; i < G; i++) {
+        const int g = backward ? (G - 1 - i) : i;
+        if (i + 1 < G) stream_load<T>(nxt, st, pr, backward ? (g - 1) : (g + 1));   // prefetch the next kangaroo
+        u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8];
+        unpack8(x, cur.x0, cur.x1);
+        unpack8(inv, cur.p0, cur.p1);
+        const u32 j = x[0] & 31u;
+        lds_jp(jx, jpx, j);
+        fe_sub(dx, x, jx);
+        fe_mul(inv, inv, I);
+        if (i != G - 1) fe_mul(I, I, dx);
+        unpack8(y, cur.y0, cur.y1);
+        lds_jp(jy, jpy, j);
+        fe_sub(s, y, jy);
+        fe_mul(s, s, inv);
+        fe_sqr(rx, s);
+        fe_sub(rx, rx, jx);
+        fe_sub(rx, rx, x);
+        fe_sub(ry, x, rx);
+        fe_mul(ry, ry, s);
+        fe_sub(ry, ry, y);
+        st[(g * CHUNKS + 0) * T] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
+        st[(g * CHUNKS + 1) * T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
+        st[(g * CHUNKS + 2) * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
+        st[(g * CHUNKS + 3) * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
+        u32 d[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
+        d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+        st[(g * CHUNKS + 4) * T] = make_uint4(d[0], d[1], d[2], d[3]);
+        if (((rx[7] & mhi) | (rx[6] & mlo)) == 0u) {
+          const u64 kidx = (u64)tile * (T * G) + (u64)g * T + (u64)t;
+          if (kidx < p.nKangaroos) {
+            const u32 pos = atomicAdd(p.out, 1u);
+            if (pos < p.maxFound) {
+              u32* o = p.out + 1 + (size_t)pos * 14;
+#pragma unroll
+              for (int w = 0; w < 8; w++) o[w] = rx[w];
+              o[8] = d[0]; o[9] = d[1]; o[10] = d[2]; o[11] = d[3];
+              o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
+            }
+          }
+        }
+        if (!last) {
+          lds_jp(jx, jpx, rx[0] & 31u);
+          fe_sub(dx, rx, jx);
+          if (i == 0) {
+            pr[(g * 2) * T] = make_uint4(1, 0, 0, 0); pr[(g * 2 + 1) * T] = make_uint4(0, 0, 0, 0);
+            fe_copy(P, dx);
+          } else {
+            pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
+            fe_mul(P, P, dx);
+          }
+        }
+        cur = nxt;
+      }
+      backward ^= 1;
+    }
+  }
+}
+
 // ---- host AoS (kIdx order) <-> tile layout --------------------------------------------------------------
 // slot s -> tile = s / TILE, g = (s % TILE) / T, t = s % T.  Padding slots (s >= n) replicate kangaroo s % n
 // so that every tile is full of valid walkers; their DPs are dropped by the kidx < nKangaroos test.
-__global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, const uint4* d, u64 n, u64 nPadded) {
+__global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, const uint4* d, u64 n, u64 nPadded, int T, int K) {
+  const int TILE = T * K;
   u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nPadded) return;
   u64 src = s < n ? s : s % n;
@@ -251,7 +380,8 @@ __global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, cons
   dst[(g * CHUNKS + 3) * T + t] = py[2 * src + 1];
   dst[(g * CHUNKS + 4) * T + t] = d[src];
 }
-__global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d, u64 n) {
+__global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d, u64 n, int T, int K) {
+  const int TILE = T * K;
   u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   u64 tile = s / TILE; int r = (int)(s % TILE); int g = r / T, t = r % T;
@@ -263,7 +393,8 @@ __global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d
   d[s] = src[(g * CHUNKS + 4) * T + t];
 }
 struct PatchArgs { uint4 c[CHUNKS]; };
-__global__ void patch_kernel(uint4* state, u64 s, PatchArgs a) {
+__global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K) {
+  const int TILE = T * K;
   u64 tile = s / TILE; int r = (int)(s % TILE); int g = r / T, t = r % T;
   uint4* dst = state + tile * (K * CHUNKS * T);
   if (threadIdx.x < CHUNKS) dst[(g * CHUNKS + threadIdx.x) * T + t] = a.c[threadIdx.x];

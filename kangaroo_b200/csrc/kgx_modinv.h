@@ -1,14 +1,15 @@
 // kgx_modinv.h -- modular inverse mod p = 2^256 - 0x1000003D1, variable time, host+device.
 //
-// Replaces the reference's GPU/GPUMath.h:700-803 (_ModInv, DRS62 "delayed right shift" divsteps).  This
-// is an independent implementation of the Bernstein-Yang "safegcd" divstep iteration in batches of 62
-// steps on signed 62-bit limbs (2x2 transition matrices applied to (f,g) and (d,e)); the result
-// contract is the reference's: the canonical inverse in [0,p), and inv(0) = 0
-// (GPUMath.h:785-801, IntMod.cpp:560-569).
+// Replaces the reference's GPU/GPUMath.h:700-803 (_ModInv: DRS62 "delayed right shift" divsteps on 64-bit
+// limbs, which sm_100a has to emulate).  This is an independent implementation of the Bernstein-Yang
+// "safegcd" divstep iteration sized for a 32-bit integer datapath: batches of 30 divsteps on the low words,
+// 2x2 transition matrices with 32-bit signed entries applied to (f,g) and (d,e) held as 9 signed 30-bit
+// limbs, so every product is one native 32x32->64 IMAD.WIDE.  Result contract = the reference's: the
+// canonical inverse in [0,p), and inv(0) = 0 (GPUMath.h:785-801, IntMod.cpp:560-569).
 //
-// In the jump kernel every lane of the inverting warp runs this on the SAME value (the group product
-// after the butterfly), so the data-dependent control flow is warp-uniform: no divergence.
-// Compiles as plain C++ for the CPU unit test (tests/test_modinv_host.py via csrc/kgx_hosttest.cpp).
+// In the jump kernel every lane of the inverting warp runs this on the SAME value (the tile product after
+// the butterfly), so all data-dependent control flow is warp-uniform: no divergence.
+// Compiles as plain C++ for the CPU unit test (tests/test_abi_cpu.py via csrc/kgx_hosttest.cpp).
 #pragma once
 #include <cstdint>
 
@@ -20,182 +21,165 @@
 
 namespace kgx {
 
-typedef __int128 i128;
-struct s62 { int64_t v[5]; };
-struct t2x2 { int64_t u, v, q, r; };
+struct s30 { int32_t v[9]; };
+struct t2x2 { int32_t u, v, q, r; };
 
-KGX_HD int ctz64(uint64_t x) {
+KGX_HD int ctz32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
-  return __ffsll((long long)x) - 1;
+  return __ffs((int)x) - 1;
 #else
-  return __builtin_ctzll(x);
+  return __builtin_ctz(x);
 #endif
 }
 
-// 62 divsteps on the low words; returns new eta and the transition matrix scaled by 2^62.
-KGX_HD int64_t divsteps_62_var(int64_t eta, uint64_t f0, uint64_t g0, t2x2* t) {
-  uint64_t u = 1, v = 0, q = 0, r = 1;
-  uint64_t f = f0, g = g0, m;
-  uint32_t w;
-  int i = 62, limit, zeros;
+// 30 divsteps on the low words; returns new eta and the transition matrix scaled by 2^30.
+KGX_HD int32_t divsteps_30_var(int32_t eta, uint32_t f0, uint32_t g0, t2x2* t) {
+  uint32_t u = 1, v = 0, q = 0, r = 1;
+  uint32_t f = f0, g = g0, m, w;
+  int i = 30, limit, zeros;
   for (;;) {
-    zeros = ctz64(g | (~0ULL << i));
+    zeros = ctz32(g | (0xFFFFFFFFu << i));
     g >>= zeros; u <<= zeros; v <<= zeros; eta -= zeros; i -= zeros;
     if (i == 0) break;
     if (eta < 0) {
-      uint64_t tmp;
+      uint32_t tmp;
       eta = -eta;
-      tmp = f; f = g; g = 0 - tmp;
-      tmp = u; u = q; q = 0 - tmp;
-      tmp = v; v = r; r = 0 - tmp;
-      limit = ((int)eta + 1) > i ? i : ((int)eta + 1);
-      m = (~0ULL >> (64 - limit)) & 63U;
-      w = (uint32_t)((f * g * (f * f - 2)) & m);
-    } else {
-      limit = ((int)eta + 1) > i ? i : ((int)eta + 1);
-      m = (~0ULL >> (64 - limit)) & 15U;
-      w = (uint32_t)(f + (((f + 1) & 4) << 1));
-      w = (uint32_t)((0 - (uint64_t)w) * g & m);
+      tmp = f; f = g; g = 0u - tmp;
+      tmp = u; u = q; q = 0u - tmp;
+      tmp = v; v = r; r = 0u - tmp;
     }
+    // cancel up to 6 low bits of g at once: w = -g/f mod 2^limit, with f*(f*f-2) == -1/f mod 64
+    limit = (eta + 1) > i ? i : (eta + 1);
+    m = (0xFFFFFFFFu >> (32 - limit)) & 63u;
+    w = (f * g * (f * f - 2u)) & m;
     g += f * w; q += u * w; r += v * w;
   }
-  t->u = (int64_t)u; t->v = (int64_t)v; t->q = (int64_t)q; t->r = (int64_t)r;
+  t->u = (int32_t)u; t->v = (int32_t)v; t->q = (int32_t)q; t->r = (int32_t)r;
   return eta;
 }
 
-// p in signed-62 form: p = 256*2^248 - 0x1000003D1
-#define KGX_P0 (-0x1000003D1LL)
-#define KGX_P4 (256LL)
-#define KGX_PINV62 0x27C7F6E22DDACACFULL  // p^-1 mod 2^62
+// p in signed-30 form: limbs {-977, -4, 0, 0, 0, 0, 0, 0, 65536}
+#define KGX_P0 (-977)
+#define KGX_P1 (-4)
+#define KGX_P8 (65536)
+#define KGX_PINV30 0x2DDACACFu  // p^-1 mod 2^30
 
-// (d,e) <- t * (d,e) / 2^62 mod p
-KGX_HD void update_de_62(s62* d, s62* e, const t2x2* t) {
-  const uint64_t M62 = ~0ULL >> 2;
-  const int64_t d0 = d->v[0], d1 = d->v[1], d2 = d->v[2], d3 = d->v[3], d4 = d->v[4];
-  const int64_t e0 = e->v[0], e1 = e->v[1], e2 = e->v[2], e3 = e->v[3], e4 = e->v[4];
-  const int64_t u = t->u, v = t->v, q = t->q, r = t->r;
-  int64_t md, me, sd, se;
-  i128 cd, ce;
-  sd = d4 >> 63; se = e4 >> 63;
+// (d,e) <- t * (d,e) / 2^30 mod p
+KGX_HD void update_de_30(s30* d, s30* e, const t2x2* t) {
+  const int32_t M30 = (int32_t)(0xFFFFFFFFu >> 2);
+  const int32_t u = t->u, v = t->v, q = t->q, r = t->r;
+  int32_t di, ei, md, me, sd, se;
+  int64_t cd, ce;
+  sd = d->v[8] >> 31; se = e->v[8] >> 31;
   md = (u & sd) + (v & se);
   me = (q & sd) + (r & se);
-  cd = (i128)u * d0 + (i128)v * e0;
-  ce = (i128)q * d0 + (i128)r * e0;
-  md -= (int64_t)((KGX_PINV62 * (uint64_t)cd + (uint64_t)md) & M62);
-  me -= (int64_t)((KGX_PINV62 * (uint64_t)ce + (uint64_t)me) & M62);
-  cd += (i128)KGX_P0 * md;
-  ce += (i128)KGX_P0 * me;
-  cd >>= 62; ce >>= 62;
-  cd += (i128)u * d1 + (i128)v * e1;
-  ce += (i128)q * d1 + (i128)r * e1;
-  d->v[0] = (int64_t)((uint64_t)cd & M62); cd >>= 62;
-  e->v[0] = (int64_t)((uint64_t)ce & M62); ce >>= 62;
-  cd += (i128)u * d2 + (i128)v * e2;
-  ce += (i128)q * d2 + (i128)r * e2;
-  d->v[1] = (int64_t)((uint64_t)cd & M62); cd >>= 62;
-  e->v[1] = (int64_t)((uint64_t)ce & M62); ce >>= 62;
-  cd += (i128)u * d3 + (i128)v * e3;
-  ce += (i128)q * d3 + (i128)r * e3;
-  d->v[2] = (int64_t)((uint64_t)cd & M62); cd >>= 62;
-  e->v[2] = (int64_t)((uint64_t)ce & M62); ce >>= 62;
-  cd += (i128)u * d4 + (i128)v * e4;
-  ce += (i128)q * d4 + (i128)r * e4;
-  cd += (i128)KGX_P4 * md;
-  ce += (i128)KGX_P4 * me;
-  d->v[3] = (int64_t)((uint64_t)cd & M62); cd >>= 62;
-  e->v[3] = (int64_t)((uint64_t)ce & M62); ce >>= 62;
-  d->v[4] = (int64_t)cd;
-  e->v[4] = (int64_t)ce;
+  di = d->v[0]; ei = e->v[0];
+  cd = (int64_t)u * di + (int64_t)v * ei;
+  ce = (int64_t)q * di + (int64_t)r * ei;
+  md -= (int32_t)((KGX_PINV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+  me -= (int32_t)((KGX_PINV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+  cd += (int64_t)KGX_P0 * md;
+  ce += (int64_t)KGX_P0 * me;
+  cd >>= 30; ce >>= 30;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 9; ++i) {
+    di = d->v[i]; ei = e->v[i];
+    cd += (int64_t)u * di + (int64_t)v * ei;
+    ce += (int64_t)q * di + (int64_t)r * ei;
+    if (i == 1) { cd += (int64_t)KGX_P1 * md; ce += (int64_t)KGX_P1 * me; }
+    if (i == 8) { cd += (int64_t)KGX_P8 * md; ce += (int64_t)KGX_P8 * me; }
+    d->v[i - 1] = (int32_t)cd & M30; cd >>= 30;
+    e->v[i - 1] = (int32_t)ce & M30; ce >>= 30;
+  }
+  d->v[8] = (int32_t)cd;
+  e->v[8] = (int32_t)ce;
 }
 
-// (f,g) <- t * (f,g) / 2^62 on the first len limbs
-KGX_HD void update_fg_62_var(int len, s62* f, s62* g, const t2x2* t) {
-  const uint64_t M62 = ~0ULL >> 2;
-  const int64_t u = t->u, v = t->v, q = t->q, r = t->r;
-  int64_t fi, gi;
-  i128 cf, cg;
+// (f,g) <- t * (f,g) / 2^30 on the first len limbs
+template <int LEN>
+KGX_HD void update_fg_30(s30* f, s30* g, const t2x2* t) {
+  const int32_t M30 = (int32_t)(0xFFFFFFFFu >> 2);
+  const int32_t u = t->u, v = t->v, q = t->q, r = t->r;
+  int32_t fi, gi;
+  int64_t cf, cg;
   fi = f->v[0]; gi = g->v[0];
-  cf = (i128)u * fi + (i128)v * gi;
-  cg = (i128)q * fi + (i128)r * gi;
-  cf >>= 62; cg >>= 62;
-  for (int i = 1; i < len; ++i) {
+  cf = (int64_t)u * fi + (int64_t)v * gi;
+  cg = (int64_t)q * fi + (int64_t)r * gi;
+  cf >>= 30; cg >>= 30;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < LEN; ++i) {
     fi = f->v[i]; gi = g->v[i];
-    cf += (i128)u * fi + (i128)v * gi;
-    cg += (i128)q * fi + (i128)r * gi;
-    f->v[i - 1] = (int64_t)((uint64_t)cf & M62); cf >>= 62;
-    g->v[i - 1] = (int64_t)((uint64_t)cg & M62); cg >>= 62;
+    cf += (int64_t)u * fi + (int64_t)v * gi;
+    cg += (int64_t)q * fi + (int64_t)r * gi;
+    f->v[i - 1] = (int32_t)cf & M30; cf >>= 30;
+    g->v[i - 1] = (int32_t)cg & M30; cg >>= 30;
   }
-  f->v[len - 1] = (int64_t)cf;
-  g->v[len - 1] = (int64_t)cg;
+  f->v[LEN - 1] = (int32_t)cf;
+  g->v[LEN - 1] = (int32_t)cg;
 }
 
 // r <- r * sign(f) normalised into [0,p)
-KGX_HD void normalize_62(s62* r, int64_t sign) {
-  const int64_t M62 = (int64_t)(~0ULL >> 2);
-  int64_t r0 = r->v[0], r1 = r->v[1], r2 = r->v[2], r3 = r->v[3], r4 = r->v[4];
-  int64_t cond_add, cond_negate;
-  cond_add = r4 >> 63;
-  r0 += KGX_P0 & cond_add;
-  r4 += KGX_P4 & cond_add;
-  cond_negate = sign >> 63;
-  r0 = (r0 ^ cond_negate) - cond_negate;
-  r1 = (r1 ^ cond_negate) - cond_negate;
-  r2 = (r2 ^ cond_negate) - cond_negate;
-  r3 = (r3 ^ cond_negate) - cond_negate;
-  r4 = (r4 ^ cond_negate) - cond_negate;
-  r1 += r0 >> 62; r0 &= M62;
-  r2 += r1 >> 62; r1 &= M62;
-  r3 += r2 >> 62; r2 &= M62;
-  r4 += r3 >> 62; r3 &= M62;
-  cond_add = r4 >> 63;
-  r0 += KGX_P0 & cond_add;
-  r4 += KGX_P4 & cond_add;
-  r1 += r0 >> 62; r0 &= M62;
-  r2 += r1 >> 62; r1 &= M62;
-  r3 += r2 >> 62; r2 &= M62;
-  r4 += r3 >> 62; r3 &= M62;
-  r->v[0] = r0; r->v[1] = r1; r->v[2] = r2; r->v[3] = r3; r->v[4] = r4;
+KGX_HD void normalize_30(s30* r, int32_t sign) {
+  const int32_t M30 = (int32_t)(0xFFFFFFFFu >> 2);
+  int32_t r0 = r->v[0], r1 = r->v[1], r2 = r->v[2], r3 = r->v[3], r4 = r->v[4], r5 = r->v[5], r6 = r->v[6], r7 = r->v[7],
+          r8 = r->v[8];
+  int32_t cond_add, cond_negate;
+  cond_add = r8 >> 31;
+  r0 += KGX_P0 & cond_add; r1 += KGX_P1 & cond_add; r8 += KGX_P8 & cond_add;
+  cond_negate = sign >> 31;
+  r0 = (r0 ^ cond_negate) - cond_negate; r1 = (r1 ^ cond_negate) - cond_negate; r2 = (r2 ^ cond_negate) - cond_negate;
+  r3 = (r3 ^ cond_negate) - cond_negate; r4 = (r4 ^ cond_negate) - cond_negate; r5 = (r5 ^ cond_negate) - cond_negate;
+  r6 = (r6 ^ cond_negate) - cond_negate; r7 = (r7 ^ cond_negate) - cond_negate; r8 = (r8 ^ cond_negate) - cond_negate;
+  r1 += r0 >> 30; r0 &= M30; r2 += r1 >> 30; r1 &= M30; r3 += r2 >> 30; r2 &= M30; r4 += r3 >> 30; r3 &= M30;
+  r5 += r4 >> 30; r4 &= M30; r6 += r5 >> 30; r5 &= M30; r7 += r6 >> 30; r6 &= M30; r8 += r7 >> 30; r7 &= M30;
+  cond_add = r8 >> 31;
+  r0 += KGX_P0 & cond_add; r1 += KGX_P1 & cond_add; r8 += KGX_P8 & cond_add;
+  r1 += r0 >> 30; r0 &= M30; r2 += r1 >> 30; r1 &= M30; r3 += r2 >> 30; r2 &= M30; r4 += r3 >> 30; r3 &= M30;
+  r5 += r4 >> 30; r4 &= M30; r6 += r5 >> 30; r5 &= M30; r7 += r6 >> 30; r6 &= M30; r8 += r7 >> 30; r7 &= M30;
+  r->v[0] = r0; r->v[1] = r1; r->v[2] = r2; r->v[3] = r3; r->v[4] = r4; r->v[5] = r5; r->v[6] = r6; r->v[7] = r7; r->v[8] = r8;
 }
 
-// x: 4 x u64 little-endian (any value < 2^256); out: canonical inverse, 0 -> 0.
-KGX_HD void modinv256(uint64_t out[4], const uint64_t in[4]) {
-  const uint64_t M62 = ~0ULL >> 2;
-  s62 d = {{0, 0, 0, 0, 0}}, e = {{1, 0, 0, 0, 0}};
-  s62 f = {{KGX_P0, 0, 0, 0, KGX_P4}};
-  s62 g;
-  g.v[0] = (int64_t)(in[0] & M62);
-  g.v[1] = (int64_t)(((in[0] >> 62) | (in[1] << 2)) & M62);
-  g.v[2] = (int64_t)(((in[1] >> 60) | (in[2] << 4)) & M62);
-  g.v[3] = (int64_t)(((in[2] >> 58) | (in[3] << 6)) & M62);
-  g.v[4] = (int64_t)(in[3] >> 56);
-  int len = 5;
-  int64_t eta = -1;
-  for (int it = 0; it < 24; ++it) {   // 12 batches bound 256-bit inputs; 24 is a safety net
+// in/out: 8 x u32 little-endian words (any value < 2^256); out: canonical inverse, 0 -> 0.
+KGX_HD void modinv256(uint32_t out[8], const uint32_t in[8]) {
+  const uint32_t M30 = 0xFFFFFFFFu >> 2;
+  s30 d = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}, e = {{1, 0, 0, 0, 0, 0, 0, 0, 0}};
+  s30 f = {{KGX_P0, KGX_P1, 0, 0, 0, 0, 0, 0, KGX_P8}};
+  s30 g;
+  // 8 x 32 -> 9 x 30
+  g.v[0] = (int32_t)(in[0] & M30);
+  g.v[1] = (int32_t)(((in[0] >> 30) | (in[1] << 2)) & M30);
+  g.v[2] = (int32_t)(((in[1] >> 28) | (in[2] << 4)) & M30);
+  g.v[3] = (int32_t)(((in[2] >> 26) | (in[3] << 6)) & M30);
+  g.v[4] = (int32_t)(((in[3] >> 24) | (in[4] << 8)) & M30);
+  g.v[5] = (int32_t)(((in[4] >> 22) | (in[5] << 10)) & M30);
+  g.v[6] = (int32_t)(((in[5] >> 20) | (in[6] << 12)) & M30);
+  g.v[7] = (int32_t)(((in[6] >> 18) | (in[7] << 14)) & M30);
+  g.v[8] = (int32_t)(in[7] >> 16);
+  int32_t eta = -1;
+  // full-length updates keep every loop fully unrolled with static register indexing (no local memory);
+  // the batch count is data dependent (about 18 for random input; 25 bounds any 256-bit input).
+  for (int it = 0; it < 40; ++it) {
     t2x2 t;
-    eta = divsteps_62_var(eta, (uint64_t)f.v[0], (uint64_t)g.v[0], &t);
-    update_de_62(&d, &e, &t);
-    update_fg_62_var(len, &f, &g, &t);
-    if (g.v[0] == 0) {
-      int64_t cond = 0;
-      for (int j = 1; j < len; ++j) cond |= g.v[j];
-      if (cond == 0) break;
-    }
-    int64_t fn = f.v[len - 1], gn = g.v[len - 1];
-    int64_t cond = ((int64_t)len - 2) >> 63;
-    cond |= fn ^ (fn >> 63);
-    cond |= gn ^ (gn >> 63);
-    if (cond == 0) {
-      f.v[len - 2] |= (int64_t)((uint64_t)fn << 62);
-      g.v[len - 2] |= (int64_t)((uint64_t)gn << 62);
-      --len;
-    }
+    eta = divsteps_30_var(eta, (uint32_t)f.v[0], (uint32_t)g.v[0], &t);
+    update_de_30(&d, &e, &t);
+    update_fg_30<9>(&f, &g, &t);
+    int32_t cond = g.v[0] | g.v[1] | g.v[2] | g.v[3] | g.v[4] | g.v[5] | g.v[6] | g.v[7] | g.v[8];
+    if (cond == 0) break;
   }
-  // gcd is |f| = 1 for invertible input; for input 0 (or a multiple of p) f = +-p and d = 0.
-  normalize_62(&d, f.v[len - 1]);
-  out[0] = (uint64_t)d.v[0] | ((uint64_t)d.v[1] << 62);
-  out[1] = ((uint64_t)d.v[1] >> 2) | ((uint64_t)d.v[2] << 60);
-  out[2] = ((uint64_t)d.v[2] >> 4) | ((uint64_t)d.v[3] << 58);
-  out[3] = ((uint64_t)d.v[3] >> 6) | ((uint64_t)d.v[4] << 56);
+  // gcd is |f| = 1 for invertible input; for 0 (or a multiple of p) f = +-p and d = 0.
+  normalize_30(&d, f.v[8]);
+  out[0] = (uint32_t)d.v[0] | ((uint32_t)d.v[1] << 30);
+  out[1] = ((uint32_t)d.v[1] >> 2) | ((uint32_t)d.v[2] << 28);
+  out[2] = ((uint32_t)d.v[2] >> 4) | ((uint32_t)d.v[3] << 26);
+  out[3] = ((uint32_t)d.v[3] >> 6) | ((uint32_t)d.v[4] << 24);
+  out[4] = ((uint32_t)d.v[4] >> 8) | ((uint32_t)d.v[5] << 22);
+  out[5] = ((uint32_t)d.v[5] >> 10) | ((uint32_t)d.v[6] << 20);
+  out[6] = ((uint32_t)d.v[6] >> 12) | ((uint32_t)d.v[7] << 18);
+  out[7] = ((uint32_t)d.v[7] >> 14) | ((uint32_t)d.v[8] << 16);
 }
 
 }  // namespace kgx
