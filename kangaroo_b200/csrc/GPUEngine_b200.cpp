@@ -1,0 +1,162 @@
+// GPUEngine_b200.cpp -- drop-in implementation of the reference's `class GPUEngine` on top of libkgx.so.
+//
+// The class declaration is the reference's own, UNCHANGED header GPU/GPUEngine.h:40-84 (found on the include path
+// at build time: -I/root/reference; this file replaces GPU/GPUEngine.cu in the link).  Every member keeps the
+// semantics documented in SURVEY.md 8(b); the private data members of the verbatim header are reused as opaque
+// storage (inputKangaroo -> kgx_engine*, outputItemPinned -> kgx_item staging) because the header cannot change.
+//
+// With this object and libkgx.so the reference's main.cpp / Kangaroo.cpp / Check.cpp / HashTable.cpp / SECPK1 build
+// and run unmodified:  see kangaroo_b200/csrc/build_dropin.sh and INTEGRATION.md.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "GPU/GPUEngine.h"
+#include "../../include/kgx.h"
+
+#define KGX(e) (reinterpret_cast<kgx_engine*>(e))
+
+static void int_to_limbs(uint64_t* dst, Int* v, int limbs) { for (int i = 0; i < limbs; i++) dst[i] = v->bits64[i]; }
+
+void GPUEngine::SetWildOffset(Int* offset) { wildOffset.Set(offset); }        // GPUEngine.cu:140-142
+
+GPUEngine::GPUEngine(int nbThreadGroup, int nbThreadPerGroup, int gpuId, uint32_t maxFound) {   // GPUEngine.cu:144-253
+  this->nbThreadPerGroup = nbThreadPerGroup;
+  this->nbThread = nbThreadGroup * nbThreadPerGroup;
+  this->maxFound = maxFound;
+  this->outputSize = maxFound * ITEM_SIZE + 4;
+  initialised = false; lostWarning = false;
+  inputKangaroo = NULL; inputKangarooPinned = NULL; outputItem = NULL; outputItemPinned = NULL; jumpPinned = NULL;
+  kangarooSize = 0; kangarooSizePinned = 0; jumpSize = NB_JUMP * 8 * 4; dpMask = 0;
+  wildOffset.SetInt32(0);
+  kgx_engine* e = kgx_create(gpuId, nbThreadGroup, nbThreadPerGroup, maxFound);
+  if (!e) { printf("GPUEngine: %s\n", kgx_last_error(NULL)); return; }        // callers never check (Kangaroo.cpp:523-526)
+  inputKangaroo = reinterpret_cast<uint64_t*>(e);
+  outputItemPinned = reinterpret_cast<uint32_t*>(new kgx_item[maxFound]);
+  kangarooSize = (uint32_t)kgx_memory_bytes(e);
+  char info[256] = "", name[200] = "?"; int sms = 0;
+  if (kgx_device_info(gpuId, info, sizeof info) == 0) { char* bar = strchr(info, '|'); if (bar) { *bar = 0; sms = atoi(bar + 1); } strncpy(name, info, sizeof name - 1); }
+  char tmp[512];
+  snprintf(tmp, sizeof tmp, "GPU #%d %s (%dx%d cores) Grid(%dx%d)", gpuId, name, sms, 128, nbThreadGroup, nbThreadPerGroup);
+  deviceName = std::string(tmp);
+  initialised = true;
+}
+
+GPUEngine::~GPUEngine() {
+  if (inputKangaroo) kgx_destroy(KGX(inputKangaroo));
+  if (outputItemPinned) delete[] reinterpret_cast<kgx_item*>(outputItemPinned);
+}
+
+int GPUEngine::GetMemory() { return (int)(inputKangaroo ? kgx_memory_bytes(KGX(inputKangaroo)) : 0); }   // int, as the reference (overflows > 2 GB)
+int GPUEngine::GetGroupSize() { return GPU_GRP_SIZE; }
+int GPUEngine::GetNbThread() { return nbThread; }
+
+bool GPUEngine::GetGridSize(int gpuId, int* x, int* y) {                       // GPUEngine.cu:275-309
+  if (*x <= 0 || *y <= 0) {
+    if (kgx_device_count() == 0) { printf("GPUEngine: There are no available device(s) that support CUDA\n"); return false; }
+    if (kgx_grid_default(gpuId, x, y) != 0) { printf("GPUEngine::GetGridSize() Invalid gpuId\n"); return false; }
+  }
+  return true;
+}
+
+void* GPUEngine::AllocatePinnedMemory(size_t size) { return malloc(size); }    // unused by every caller
+void GPUEngine::FreePinnedMemory(void* buff) { free(buff); }
+
+void GPUEngine::PrintCudaInfo() {                                              // GPUEngine.cu:331-375 (-l)
+  int n = kgx_device_count();
+  if (n == 0) { printf("GPUEngine: There are no available device(s) that support CUDA\n"); return; }
+  for (int i = 0; i < n; i++) {
+    char info[256];
+    if (kgx_device_info(i, info, sizeof info) != 0) continue;
+    char name[200]; int sms, maj, min; double mb;
+    char* p = strchr(info, '|'); *p = 0; strncpy(name, info, sizeof name - 1); name[sizeof name - 1] = 0;
+    sscanf(p + 1, "%d|%d|%d|%lf", &sms, &maj, &min, &mb);
+    printf("GPU #%d %s (%dx%d cores) (Cap %d.%d) (%.1f MB) (%s)\n", i, name, sms, 128, maj, min, mb, "Multiple host threads");
+  }
+}
+
+void GPUEngine::SetParams(uint64_t dpMask, Int* distance, Int* px, Int* py) {  // GPUEngine.cu:559-590
+  this->dpMask = dpMask;
+  if (!inputKangaroo) return;
+  uint64_t jd[NB_JUMP * 2], jx[NB_JUMP * 4], jy[NB_JUMP * 4];
+  for (int i = 0; i < NB_JUMP; i++) { int_to_limbs(jd + 2 * i, &distance[i], 2); int_to_limbs(jx + 4 * i, &px[i], 4); int_to_limbs(jy + 4 * i, &py[i], 4); }
+  if (kgx_set_params(KGX(inputKangaroo), dpMask, jd, jx, jy) != 0) printf("GPUEngine: SetParams: %s\n", kgx_last_error(KGX(inputKangaroo)));
+}
+
+void GPUEngine::SetKangaroos(Int* px, Int* py, Int* d) {                        // GPUEngine.cu:381-433
+  if (!inputKangaroo) return;
+  const uint64_t n = kgx_num_kangaroos(KGX(inputKangaroo));
+  std::vector<uint64_t> ax(n * 4), ay(n * 4), ad(n * 2);
+  for (uint64_t i = 0; i < n; i++) {
+    int_to_limbs(&ax[4 * i], &px[i], 4); int_to_limbs(&ay[4 * i], &py[i], 4);
+    Int dOff; dOff.Set(&d[i]);
+    if (i % 2 == WILD) dOff.ModAddK1order(&wildOffset);
+    ad[2 * i] = dOff.bits64[0]; ad[2 * i + 1] = dOff.bits64[1];
+  }
+  if (kgx_upload(KGX(inputKangaroo), ax.data(), ay.data(), ad.data()) != 0) printf("GPUEngine: SetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo)));
+}
+
+void GPUEngine::GetKangaroos(Int* px, Int* py, Int* d) {                        // GPUEngine.cu:435-491
+  if (!inputKangaroo) { printf("GPUEngine: GetKangaroos: Cannot retreive kangaroos, mem has been freed\n"); return; }
+  const uint64_t n = kgx_num_kangaroos(KGX(inputKangaroo));
+  std::vector<uint64_t> ax(n * 4), ay(n * 4), ad(n * 2);
+  if (kgx_download(KGX(inputKangaroo), ax.data(), ay.data(), ad.data()) != 0) { printf("GPUEngine: GetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo))); return; }
+  for (uint64_t i = 0; i < n; i++) {
+    for (int k = 0; k < 4; k++) { px[i].bits64[k] = ax[4 * i + k]; py[i].bits64[k] = ay[4 * i + k]; }
+    px[i].bits64[4] = 0; py[i].bits64[4] = 0;
+    Int dOff; dOff.SetInt32(0);
+    dOff.bits64[0] = ad[2 * i]; dOff.bits64[1] = ad[2 * i + 1];
+    if (i % 2 == WILD) dOff.ModSubK1order(&wildOffset);
+    d[i].Set(&dOff);
+  }
+}
+
+void GPUEngine::SetKangaroo(uint64_t kIdx, Int* px, Int* py, Int* d) {          // GPUEngine.cu:493-538
+  if (!inputKangaroo) return;
+  uint64_t x[4], y[4], dd[2];
+  int_to_limbs(x, px, 4); int_to_limbs(y, py, 4);
+  Int dOff; dOff.Set(d);
+  if (kIdx % 2 == WILD) dOff.ModAddK1order(&wildOffset);
+  dd[0] = dOff.bits64[0]; dd[1] = dOff.bits64[1];
+  if (kgx_patch(KGX(inputKangaroo), kIdx, x, y, dd) != 0) printf("GPUEngine: SetKangaroo: %s\n", kgx_last_error(KGX(inputKangaroo)));
+}
+
+bool GPUEngine::callKernel() {                                                  // GPUEngine.cu:540-557
+  if (!inputKangaroo) return false;
+  if (kgx_launch_async(KGX(inputKangaroo)) != 0) { printf("GPUEngine: Kernel: %s\n", kgx_last_error(KGX(inputKangaroo))); return false; }
+  return true;
+}
+
+bool GPUEngine::callKernelAndWait() {                                           // GPUEngine.cu:592-605
+  bool ok = callKernel();
+  if (inputKangaroo && kgx_sync(KGX(inputKangaroo)) != 0) { printf("GPUEngine: callKernelAndWait: %s\n", kgx_last_error(KGX(inputKangaroo))); return false; }
+  return ok;
+}
+
+bool GPUEngine::Launch(std::vector<ITEM>& hashFound, bool spinWait) {            // GPUEngine.cu:607-679
+  hashFound.clear();
+  if (!inputKangaroo) return false;
+  kgx_item* items = reinterpret_cast<kgx_item*>(outputItemPinned);
+  uint32_t nItems = 0, nFound = 0;
+  // waits for the launch in flight, starts the next one, then reads the finished slab back (double buffered)
+  if (kgx_collect(KGX(inputKangaroo), items, maxFound, &nItems, &nFound, spinWait ? 1 : 0, 1) != 0) {
+    printf("GPUEngine: Launch: %s\n", kgx_last_error(KGX(inputKangaroo)));
+    return false;
+  }
+  if (nFound > maxFound && !lostWarning) {
+    printf("\nWarning, %d items lost\nHint: Search with less threads (-g) or increse dp (-d)\n", (nFound - maxFound));
+    lostWarning = true;
+  }
+  hashFound.reserve(nItems);
+  for (uint32_t i = 0; i < nItems; i++) {
+    ITEM it;
+    it.kIdx = items[i].kidx;
+    for (int k = 0; k < 4; k++) it.x.bits64[k] = items[i].x[k];
+    it.x.bits64[4] = 0;
+    it.d.bits64[0] = items[i].d[0]; it.d.bits64[1] = items[i].d[1];
+    it.d.bits64[2] = 0; it.d.bits64[3] = 0; it.d.bits64[4] = 0;
+    if (it.kIdx % 2 == WILD) it.d.ModSubK1order(&wildOffset);
+    hashFound.push_back(it);
+  }
+  return true;
+}

@@ -64,7 +64,7 @@ static const int g_ncfg = sizeof(g_cfgs) / sizeof(g_cfgs[0]);
 #define KGX_DEFAULT_CFG 0
 #endif
 #ifndef KGX_DEFAULT_STREAM
-#define KGX_DEFAULT_STREAM 0
+#define KGX_DEFAULT_STREAM 1   // streaming kernel is the faster one on B200 (profiles/r1_sweep.txt); KGX_MODE=resident selects the tile kernel
 #endif
 
 extern "C" {
@@ -146,7 +146,12 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
     if (mode && strcmp(mode, "stream") && strcmp(mode, "resident")) {
       snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream or resident"); delete e; return nullptr;
     }
-    if (e->streamMode) { e->T = 128; e->K = 128; e->smemBytes = 0; e->ctasPerSM = 2; }
+    if (e->streamMode) {
+      int g = 128;
+      if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
+      if (g != 128 && g != 96 && g != 64 && g != 192 && g != 256) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_G must be 64, 96, 128, 192 or 256"); delete e; return nullptr; }
+      e->T = 128; e->K = g; e->smemBytes = 0; e->ctasPerSM = g == 64 ? 4 : (g == 96 ? 3 : 2);
+    }
   }
   const u64 TILE = (u64)e->T * e->K;
   e->numTiles = (u32)((e->n + TILE - 1) / TILE);
@@ -280,7 +285,13 @@ int kgx_launch_async(kgx_engine* e) {
   CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
   u32 grid = (u32)(e->ctasPerSM * e->sms);
   if (grid > e->numTiles) grid = e->numTiles;
-  if (e->streamMode) stream_kernel<128, 128><<<grid, 128, 0, e->stream>>>(p);
+  if (e->streamMode) {
+    if (e->K == 64) stream_kernel<128, 64, 4><<<grid, 128, 0, e->stream>>>(p);
+    else if (e->K == 96) stream_kernel<128, 96, 3><<<grid, 128, 0, e->stream>>>(p);
+    else if (e->K == 192) stream_kernel<128, 192, 2><<<grid, 128, 0, e->stream>>>(p);
+    else if (e->K == 256) stream_kernel<128, 256, 2><<<grid, 128, 0, e->stream>>>(p);
+    else stream_kernel<128, 128, 2><<<grid, 128, 0, e->stream>>>(p);
+  }
   else g_cfgs[e->cfg].kern<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   e->launches++;
   CK(e, cudaGetLastError());

@@ -18,52 +18,19 @@ typedef uint64_t u64;
 
 #define KGX_C 0x3D1u  // 0x1000003D1 = 2^32 + 0x3D1
 
-// acc[0..7] += {a0,a2,a4,a6} * b at 64-bit aligned column pairs, carry out added into acc[8].
-__device__ __forceinline__ void kgx_mad_row(u32* acc, u32 a0, u32 a2, u32 a4, u32 a6, u32 b) {
-  asm("mad.lo.cc.u32  %0, %9, %13, %0;\n\t"
-      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
-      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
-      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
-      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
-      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
-      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
-      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-      "addc.u32       %8, %8, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
-        "+r"(acc[7]), "+r"(acc[8])
-      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
-}
+#include "kgx_chains.cuh"   // generated carry-chain primitives kgx_chain_{pairs}_{fresh words}_{carry: a|n|x}
 
-// 512 -> 256 fold, see header comment. w[16] little-endian 32-bit words.
-__device__ __forceinline__ void kgx_fold(u32* r, const u32* w) {
-  u32 r0, r1, r2, r3, r4, r5, r6, r7, r8, r9;
+// 512 -> 256 fold, see header comment. w[16] little-endian 32-bit words (w is consumed).
+__device__ __forceinline__ void kgx_fold(u32* r, u32* w) {
   const u32 c = KGX_C;
-  // r[0..8] = w[0..7] + {h0,h2,h4,h6} * c   (h = w[8..15])
-  asm("mad.lo.cc.u32  %0, %9, %13, %14;\n\t"
-      "madc.hi.cc.u32 %1, %9, %13, %15;\n\t"
-      "madc.lo.cc.u32 %2, %10, %13, %16;\n\t"
-      "madc.hi.cc.u32 %3, %10, %13, %17;\n\t"
-      "madc.lo.cc.u32 %4, %11, %13, %18;\n\t"
-      "madc.hi.cc.u32 %5, %11, %13, %19;\n\t"
-      "madc.lo.cc.u32 %6, %12, %13, %20;\n\t"
-      "madc.hi.cc.u32 %7, %12, %13, %21;\n\t"
-      "addc.u32       %8, 0, 0;"
-      : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3), "=&r"(r4), "=&r"(r5), "=&r"(r6), "=&r"(r7), "=&r"(r8)
-      : "r"(w[8]), "r"(w[10]), "r"(w[12]), "r"(w[14]), "r"(c), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
-        "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]));
-  // r[1..9] += {h1,h3,h5,h7} * c
-  asm("mad.lo.cc.u32  %0, %9, %13, %0;\n\t"
-      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
-      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
-      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
-      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
-      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
-      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
-      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-      "addc.u32       %8, 0, 0;"
-      : "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(r8), "=r"(r9)
-      : "r"(w[9]), "r"(w[11]), "r"(w[13]), "r"(w[15]), "r"(c));
-  // r[1..9] += h   (the 2^32 part of 0x1000003D1)
+  // E' = w[0..7] + {h0,h2,h4,h6} * c  (h = w[8..15]); e8 = carry
+  u32 e[10];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = w[i];
+  kgx_chain_4_0_n(e, c, w[8], w[10], w[12], w[14]);
+  // O' = {h1,h3,h5,h7} * c at words 1..8, then + h (the 2^32 part of 0x1000003D1, also at words 1..8)
+  u32 o[9];
+  kgx_chain_4_8_x(o, c, w[9], w[11], w[13], w[15]);
   asm("add.cc.u32  %0, %0, %9;\n\t"
       "addc.cc.u32 %1, %1, %10;\n\t"
       "addc.cc.u32 %2, %2, %11;\n\t"
@@ -72,10 +39,22 @@ __device__ __forceinline__ void kgx_fold(u32* r, const u32* w) {
       "addc.cc.u32 %5, %5, %14;\n\t"
       "addc.cc.u32 %6, %6, %15;\n\t"
       "addc.cc.u32 %7, %7, %16;\n\t"
-      "addc.u32    %8, %8, 0;"
-      : "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(r8), "+r"(r9)
+      "addc.u32    %8, 0, 0;"
+      : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "=&r"(o[8])
       : "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]));
-  // second fold: top = r8 + r9*2^32 ; V = top*(2^32+c) = r8*c + (r8 + r9*c)*2^32 + r9*2^64 ; r[0..7] += V (carry dropped)
+  // R1 = E' + (O'' << 32): words 1..9
+  asm("add.cc.u32  %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %11;\n\t"
+      "addc.cc.u32 %3, %3, %12;\n\t"
+      "addc.cc.u32 %4, %4, %13;\n\t"
+      "addc.cc.u32 %5, %5, %14;\n\t"
+      "addc.cc.u32 %6, %6, %15;\n\t"
+      "addc.cc.u32 %7, %7, %16;\n\t"
+      "addc.u32    %8, %17, 0;"
+      : "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "=&r"(e[9])
+      : "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]));
+  // second fold: top = e8 + e9*2^32 ; V = top*(2^32+c) = e8*c + (e8 + e9*c)*2^32 + e9*2^64 ; r = R1[0..7] + V (carry dropped)
   u32 v0, v1, v2;
   asm("{\n\t"
       ".reg .u32 ulo, uhi;\n\t"
@@ -87,7 +66,7 @@ __device__ __forceinline__ void kgx_fold(u32* r, const u32* w) {
       "addc.u32       %2, %4, uhi;\n\t"
       "}"
       : "=&r"(v0), "=&r"(v1), "=&r"(v2)
-      : "r"(r8), "r"(r9), "r"(c));
+      : "r"(e[8]), "r"(e[9]), "r"(c));
   asm("add.cc.u32  %0, %0, %8;\n\t"
       "addc.cc.u32 %1, %1, %9;\n\t"
       "addc.cc.u32 %2, %2, %10;\n\t"
@@ -96,13 +75,14 @@ __device__ __forceinline__ void kgx_fold(u32* r, const u32* w) {
       "addc.cc.u32 %5, %5, 0;\n\t"
       "addc.cc.u32 %6, %6, 0;\n\t"
       "addc.u32    %7, %7, 0;"
-      : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7])
       : "r"(v0), "r"(v1), "r"(v2));
-  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5; r[6] = r6; r[7] = r7;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = e[i];
 }
 
-// w[0..15] = E + (O << 32) where E[i] sits at word i and O[i] at word i+1.
-__device__ __forceinline__ void kgx_merge_eo(u32* w, const u32* E, const u32* O) {
+// w[0..15] = E + (O << 32) where E[i] sits at word i and O[i] at word i+1 (E15 may be passed as 0).
+__device__ __forceinline__ void kgx_merge_eo(u32* w, const u32* E, u32 E15, const u32* O) {
   w[0] = E[0];
   asm("add.cc.u32  %0, %15, %30;\n\t"
       "addc.cc.u32 %1, %16, %31;\n\t"
@@ -122,26 +102,32 @@ __device__ __forceinline__ void kgx_merge_eo(u32* w, const u32* E, const u32* O)
       : "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(w[8]),
         "=&r"(w[9]), "=&r"(w[10]), "=&r"(w[11]), "=&r"(w[12]), "=&r"(w[13]), "=&r"(w[14]), "=&r"(w[15])
       : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
-        "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E15),
         "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
         "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
 }
 
-// 256 x 256 -> 512 schoolbook on the even/odd split.
+// 256 x 256 -> 512 schoolbook on the even/odd column split; every accumulator word is written before it is
+// read (no zero-initialisation), every row is one carry chain.
 __device__ __forceinline__ void kgx_mul512(u32* w, const u32* a, const u32* b) {
-  u32 E[17], O[15];
-#pragma unroll
-  for (int i = 0; i < 17; i++) E[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 15; i++) O[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    kgx_mad_row(E + i, a[0], a[2], a[4], a[6], b[i]);          // row i,   even j -> even columns
-    kgx_mad_row(O + i, a[1], a[3], a[5], a[7], b[i]);          // row i,   odd  j -> odd columns
-    kgx_mad_row(E + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);  // row i+1, odd  j -> even columns
-    kgx_mad_row(O + i, a[0], a[2], a[4], a[6], b[i + 1]);      // row i+1, even j -> odd columns
-  }
-  kgx_merge_eo(w, E, O);
+  u32 E[16], O[15];
+  kgx_chain_4_8_x(E + 0, b[0], a[0], a[2], a[4], a[6]);   // row 0 even j -> words 0..7   (all new)
+  kgx_chain_4_8_x(O + 0, b[0], a[1], a[3], a[5], a[7]);   // row 0 odd  j -> words 1..8   (all new)
+  kgx_chain_4_2_n(E + 2, b[1], a[1], a[3], a[5], a[7]);   // row 1 odd  j -> words 2..9,  E8 E9 new, carry -> E10 new
+  kgx_chain_4_0_n(O + 0, b[1], a[0], a[2], a[4], a[6]);   // row 1 even j -> words 1..8,  carry -> O8 new
+  kgx_chain_4_0_a(E + 2, b[2], a[0], a[2], a[4], a[6]);   // row 2
+  kgx_chain_4_1_n(O + 2, b[2], a[1], a[3], a[5], a[7]);   //        O9 new, carry -> O10 new
+  kgx_chain_4_1_n(E + 4, b[3], a[1], a[3], a[5], a[7]);   // row 3  E11 new, carry -> E12 new
+  kgx_chain_4_0_a(O + 2, b[3], a[0], a[2], a[4], a[6]);
+  kgx_chain_4_0_a(E + 4, b[4], a[0], a[2], a[4], a[6]);   // row 4
+  kgx_chain_4_1_n(O + 4, b[4], a[1], a[3], a[5], a[7]);   //        O11 new, carry -> O12 new
+  kgx_chain_4_1_n(E + 6, b[5], a[1], a[3], a[5], a[7]);   // row 5  E13 new, carry -> E14 new
+  kgx_chain_4_0_a(O + 4, b[5], a[0], a[2], a[4], a[6]);
+  kgx_chain_4_0_a(E + 6, b[6], a[0], a[2], a[4], a[6]);   // row 6
+  kgx_chain_4_1_n(O + 6, b[6], a[1], a[3], a[5], a[7]);   //        O13 new, carry -> O14 new
+  kgx_chain_4_1_x(E + 8, b[7], a[1], a[3], a[5], a[7]);   // row 7  E15 new, no carry out of word 15
+  kgx_chain_4_0_a(O + 6, b[7], a[0], a[2], a[4], a[6]);
+  kgx_merge_eo(w, E, E[15], O);
 }
 
 __device__ __forceinline__ void fe_mul(u32* r, const u32* a, const u32* b) {
@@ -150,105 +136,73 @@ __device__ __forceinline__ void fe_mul(u32* r, const u32* a, const u32* b) {
   kgx_fold(r, w);
 }
 
-// carry chains of 1..3 column pairs (kgx_mad_row is the 4-pair form): acc[0..2n-1] += {a...} * b, carry into acc[2n]
-__device__ __forceinline__ void kgx_mad_c1(u32* acc, u32 b, u32 a0) {
-  asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
-      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-      "addc.u32       %2, %2, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(a0), "r"(b));
-}
-__device__ __forceinline__ void kgx_mad_c2(u32* acc, u32 b, u32 a0, u32 a1) {
-  asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
-      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
-      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
-      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
-      "addc.u32       %4, %4, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(a0), "r"(a1), "r"(b));
-}
-__device__ __forceinline__ void kgx_mad_c3(u32* acc, u32 b, u32 a0, u32 a1, u32 a2) {
-  asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
-      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
-      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
-      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
-      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
-      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
-      "addc.u32       %6, %6, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(b));
-}
-
 // a^2 as 28 cross products (computed once, doubled) + 8 squares: 36 IMAD.WIDE instead of 64.
 // Same exact 512-bit value as a*a, hence the same folded result (GPUMath.h:909-1019 / IntMod.cpp:1030-1234).
 __device__ __forceinline__ void kgx_sqr512(u32* w, const u32* a) {
   u32 E[16], O[15];
-#pragma unroll
-  for (int i = 0; i < 16; i++) E[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 15; i++) O[i] = 0;
-  // E[i] sits at word i, O[i] at word i+1; product a_i*a_j lands at word i+j
-  kgx_mad_row(O + 0, a[1], a[3], a[5], a[7], a[0]);   // 0x{1,3,5,7} -> words 1,3,5,7
-  kgx_mad_c3(E + 2, a[0], a[2], a[4], a[6]);          // 0x{2,4,6}   -> words 2,4,6
-  kgx_mad_c3(O + 2, a[1], a[2], a[4], a[6]);          // 1x{2,4,6}   -> words 3,5,7
-  kgx_mad_c3(E + 4, a[1], a[3], a[5], a[7]);          // 1x{3,5,7}   -> words 4,6,8
-  kgx_mad_c3(O + 4, a[2], a[3], a[5], a[7]);          // 2x{3,5,7}   -> words 5,7,9
-  kgx_mad_c2(E + 6, a[2], a[4], a[6]);                // 2x{4,6}     -> words 6,8
-  kgx_mad_c2(O + 6, a[3], a[4], a[6]);                // 3x{4,6}     -> words 7,9
-  kgx_mad_c2(E + 8, a[3], a[5], a[7]);                // 3x{5,7}     -> words 8,10
-  kgx_mad_c2(O + 8, a[4], a[5], a[7]);                // 4x{5,7}     -> words 9,11
-  kgx_mad_c1(E + 10, a[4], a[6]);                     // 4x6         -> word 10
-  kgx_mad_c1(O + 10, a[5], a[6]);                     // 5x6         -> word 11
-  kgx_mad_c1(E + 12, a[5], a[7]);                     // 5x7         -> word 12
-  kgx_mad_c1(O + 12, a[6], a[7]);                     // 6x7         -> word 13
-  // C = E + (O << 32), words 1..15 (word 0 is zero)
+  // E[i] sits at word i, O[i] at word i+1; product a_i*a_j lands at word i+j.  E0 E1 are never written (zero).
+  kgx_chain_4_8_x(O + 0, a[0], a[1], a[3], a[5], a[7]);   // 0x{1,3,5,7} -> words 1,3,5,7   O0..O7 new
+  kgx_chain_3_6_n(E + 2, a[0], a[2], a[4], a[6]);         // 0x{2,4,6}   -> words 2,4,6     E2..E7 new, E8 = 0
+  kgx_chain_3_0_n(O + 2, a[1], a[2], a[4], a[6]);         // 1x{2,4,6}   -> words 3,5,7     carry -> O8 new
+  kgx_chain_3_1_n(E + 4, a[1], a[3], a[5], a[7]);         // 1x{3,5,7}   -> words 4,6,8     E9 new, carry -> E10 new
+  kgx_chain_3_1_n(O + 4, a[2], a[3], a[5], a[7]);         // 2x{3,5,7}   -> words 5,7,9     O9 new, carry -> O10 new
+  kgx_chain_2_0_a(E + 6, a[2], a[4], a[6]);               // 2x{4,6}     -> words 6,8
+  kgx_chain_2_0_a(O + 6, a[3], a[4], a[6]);               // 3x{4,6}     -> words 7,9
+  kgx_chain_2_1_n(E + 8, a[3], a[5], a[7]);               // 3x{5,7}     -> words 8,10      E11 new, carry -> E12 new
+  kgx_chain_2_1_n(O + 8, a[4], a[5], a[7]);               // 4x{5,7}     -> words 9,11      O11 new, carry -> O12 new
+  kgx_chain_1_0_a(E + 10, a[4], a[6]);                    // 4x6         -> word 10
+  kgx_chain_1_0_a(O + 10, a[5], a[6]);                    // 5x6         -> word 11
+  kgx_chain_1_1_n(E + 12, a[5], a[7]);                    // 5x7         -> word 12         E13 new, carry -> E14 new
+  kgx_chain_1_1_n(O + 12, a[6], a[7]);                    // 6x7         -> word 13         O13 new, carry -> O14 new
+  // C = E + (O << 32), words 1..15 (words 0 and, from E, 1 are zero)
   u32 c[16];
-  c[0] = 0;
-  asm("add.cc.u32  %0, %15, %30;\n\t"
-      "addc.cc.u32 %1, %16, %31;\n\t"
-      "addc.cc.u32 %2, %17, %32;\n\t"
-      "addc.cc.u32 %3, %18, %33;\n\t"
-      "addc.cc.u32 %4, %19, %34;\n\t"
-      "addc.cc.u32 %5, %20, %35;\n\t"
-      "addc.cc.u32 %6, %21, %36;\n\t"
-      "addc.cc.u32 %7, %22, %37;\n\t"
-      "addc.cc.u32 %8, %23, %38;\n\t"
-      "addc.cc.u32 %9, %24, %39;\n\t"
-      "addc.cc.u32 %10, %25, %40;\n\t"
-      "addc.cc.u32 %11, %26, %41;\n\t"
-      "addc.cc.u32 %12, %27, %42;\n\t"
-      "addc.cc.u32 %13, %28, %43;\n\t"
-      "addc.u32    %14, %29, %44;"
-      : "=&r"(c[1]), "=&r"(c[2]), "=&r"(c[3]), "=&r"(c[4]), "=&r"(c[5]), "=&r"(c[6]), "=&r"(c[7]), "=&r"(c[8]),
+  c[1] = O[0];
+  asm("add.cc.u32  %0, %14, %27;\n\t"
+      "addc.cc.u32 %1, %15, %28;\n\t"
+      "addc.cc.u32 %2, %16, %29;\n\t"
+      "addc.cc.u32 %3, %17, %30;\n\t"
+      "addc.cc.u32 %4, %18, %31;\n\t"
+      "addc.cc.u32 %5, %19, %32;\n\t"
+      "addc.cc.u32 %6, %20, %33;\n\t"
+      "addc.cc.u32 %7, %21, %34;\n\t"
+      "addc.cc.u32 %8, %22, %35;\n\t"
+      "addc.cc.u32 %9, %23, %36;\n\t"
+      "addc.cc.u32 %10, %24, %37;\n\t"
+      "addc.cc.u32 %11, %25, %38;\n\t"
+      "addc.cc.u32 %12, %26, %39;\n\t"
+      "addc.u32    %13, 0, %40;"
+      : "=&r"(c[2]), "=&r"(c[3]), "=&r"(c[4]), "=&r"(c[5]), "=&r"(c[6]), "=&r"(c[7]), "=&r"(c[8]),
         "=&r"(c[9]), "=&r"(c[10]), "=&r"(c[11]), "=&r"(c[12]), "=&r"(c[13]), "=&r"(c[14]), "=&r"(c[15])
-      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
-        "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
-        "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+      : "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+        "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
         "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
-  // 2C by funnel shifts (no carry chain)
+  // 2C by funnel shifts (no carry chain); word 0 of 2C is zero
   u32 c2[16];
-  c2[0] = 0;
+  c2[1] = c[1] << 1;
 #pragma unroll
-  for (int i = 15; i >= 1; i--) c2[i] = __funnelshift_l(c[i - 1], c[i], 1);
+  for (int i = 15; i >= 2; i--) c2[i] = __funnelshift_l(c[i - 1], c[i], 1);
   // + squares a_i^2 at words (2i, 2i+1)
-  asm("mad.lo.cc.u32  %0, %16, %16, %24;\n\t"
-      "madc.hi.cc.u32 %1, %16, %16, %25;\n\t"
-      "madc.lo.cc.u32 %2, %17, %17, %26;\n\t"
-      "madc.hi.cc.u32 %3, %17, %17, %27;\n\t"
-      "madc.lo.cc.u32 %4, %18, %18, %28;\n\t"
-      "madc.hi.cc.u32 %5, %18, %18, %29;\n\t"
-      "madc.lo.cc.u32 %6, %19, %19, %30;\n\t"
-      "madc.hi.cc.u32 %7, %19, %19, %31;\n\t"
-      "madc.lo.cc.u32 %8, %20, %20, %32;\n\t"
-      "madc.hi.cc.u32 %9, %20, %20, %33;\n\t"
-      "madc.lo.cc.u32 %10, %21, %21, %34;\n\t"
-      "madc.hi.cc.u32 %11, %21, %21, %35;\n\t"
-      "madc.lo.cc.u32 %12, %22, %22, %36;\n\t"
-      "madc.hi.cc.u32 %13, %22, %22, %37;\n\t"
-      "madc.lo.cc.u32 %14, %23, %23, %38;\n\t"
-      "madc.hi.u32    %15, %23, %23, %39;"
+  asm("mul.lo.u32     %0, %16, %16;\n\t"
+      "mad.hi.cc.u32  %1, %16, %16, %24;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %25;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %26;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %27;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %28;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %29;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %30;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %31;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %32;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %33;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %34;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %35;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %36;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %37;\n\t"
+      "madc.hi.u32    %15, %23, %23, %38;"
       : "=&r"(w[0]), "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]),
         "=&r"(w[8]), "=&r"(w[9]), "=&r"(w[10]), "=&r"(w[11]), "=&r"(w[12]), "=&r"(w[13]), "=&r"(w[14]), "=&r"(w[15])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
-        "r"(c2[0]), "r"(c2[1]), "r"(c2[2]), "r"(c2[3]), "r"(c2[4]), "r"(c2[5]), "r"(c2[6]), "r"(c2[7]),
+        "r"(c2[1]), "r"(c2[2]), "r"(c2[3]), "r"(c2[4]), "r"(c2[5]), "r"(c2[6]), "r"(c2[7]),
         "r"(c2[8]), "r"(c2[9]), "r"(c2[10]), "r"(c2[11]), "r"(c2[12]), "r"(c2[13]), "r"(c2[14]), "r"(c2[15]));
 }
 

@@ -266,8 +266,65 @@ __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) 
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
 
+// One kangaroo of the fused pass (see the file header): back-substitute, jump, emit, start the next chain.
 template <int T, int G>
-__global__ void __launch_bounds__(T, 2) stream_kernel(LaunchParams p) {
+__device__ __forceinline__ void stream_body(const KangLoad& cur, uint4* st, uint4* pr, const u32* jpx, const u32* jpy,
+                                            const u32* jd, u32* I, u32* P, const int g, const int i, const bool last,
+                                            const LaunchParams& p, const u32 mlo, const u32 mhi, const u64 kbase) {
+  u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8];
+  unpack8(x, cur.x0, cur.x1);
+  unpack8(inv, cur.p0, cur.p1);
+  const u32 j = x[0] & 31u;
+  lds_jp(jx, jpx, j);
+  fe_sub(dx, x, jx);
+  fe_mul(inv, inv, I);                     // 1/dx
+  if (i != G - 1) fe_mul(I, I, dx);        // strip this dx from the running inverse
+  unpack8(y, cur.y0, cur.y1);
+  lds_jp(jy, jpy, j);
+  fe_sub(s, y, jy);
+  fe_mul(s, s, inv);                       // s = dy/dx
+  fe_sqr(rx, s);
+  fe_sub(rx, rx, jx);
+  fe_sub(rx, rx, x);                       // rx = s^2 - jx - x
+  fe_sub(ry, x, rx);
+  fe_mul(ry, ry, s);
+  fe_sub(ry, ry, y);                       // ry = s (x - rx) - y
+  st[(g * CHUNKS + 0) * T] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
+  st[(g * CHUNKS + 1) * T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
+  st[(g * CHUNKS + 2) * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
+  st[(g * CHUNKS + 3) * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
+  u32 d[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
+  d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+  st[(g * CHUNKS + 4) * T] = make_uint4(d[0], d[1], d[2], d[3]);
+  if (((rx[7] & mhi) | (rx[6] & mlo)) == 0u) {          // GPUCompute.h:96
+    const u64 kidx = kbase + (u64)g * T;
+    if (kidx < p.nKangaroos) {
+      const u32 pos = atomicAdd(p.out, 1u);
+      if (pos < p.maxFound) {                           // GPUMath.h:173-188 record layout
+        u32* o = p.out + 1 + (size_t)pos * 14;
+#pragma unroll
+        for (int w = 0; w < 8; w++) o[w] = rx[w];
+        o[8] = d[0]; o[9] = d[1]; o[10] = d[2]; o[11] = d[3];
+        o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
+      }
+    }
+  }
+  if (!last) {                             // next jump's dx and prefix, accumulated in THIS order
+    lds_jp(jx, jpx, rx[0] & 31u);
+    fe_sub(dx, rx, jx);
+    if (i == 0) {
+      pr[(g * 2) * T] = make_uint4(1, 0, 0, 0); pr[(g * 2 + 1) * T] = make_uint4(0, 0, 0, 0);
+      fe_copy(P, dx);
+    } else {
+      pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
+      fe_mul(P, P, dx);
+    }
+  }
+}
+
+template <int T, int G, int CTAS>
+__global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
+  static_assert(G % 2 == 0, "the fused pass is unrolled by two");
   __shared__ u32 sJ[JT_WORDS];
   const u32* jpx = sJ;
   const u32* jpy = sJ + 8 * 32;
@@ -280,6 +337,7 @@ __global__ void __launch_bounds__(T, 2) stream_kernel(LaunchParams p) {
   for (u32 tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
     uint4* st = p.state + (size_t)tile * (G * CHUNKS * T) + t;
     uint4* pr = p.pre + (size_t)tile * (G * 2 * T) + t;
+    const u64 kbase = (u64)tile * (T * G) + (u64)t;
     u32 P[8];
     {   // prologue: forward chain, pr[g] = product of the dx before g
       u32 x[8], jx[8], dx[8];
@@ -302,62 +360,16 @@ __global__ void __launch_bounds__(T, 2) stream_kernel(LaunchParams p) {
       u32 I[8];
       fe_inv(I, P);                              // this thread's own group: 1 / (dx_0 ... dx_{G-1})
       const bool last = (run == p.nRun - 1);
-      KangLoad cur, nxt;
-      stream_load<T>(cur, st, pr, backward ? (G - 1) : 0);
+      const int g0 = backward ? (G - 1) : 0, dg = backward ? -1 : 1;
+      KangLoad A, B;                              // ping-pong prefetch buffers (no register copies)
+      stream_load<T>(A, st, pr, g0);
 #pragma unroll 1
-      for (int i = 0; i < G; i++) {
-        const int g = backward ? (G - 1 - i) : i;
-        if (i + 1 < G) stream_load<T>(nxt, st, pr, backward ? (g - 1) : (g + 1));   // prefetch the next kangaroo
-        u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8];
-        unpack8(x, cur.x0, cur.x1);
-        unpack8(inv, cur.p0, cur.p1);
-        const u32 j = x[0] & 31u;
-        lds_jp(jx, jpx, j);
-        fe_sub(dx, x, jx);
-        fe_mul(inv, inv, I);
-        if (i != G - 1) fe_mul(I, I, dx);
-        unpack8(y, cur.y0, cur.y1);
-        lds_jp(jy, jpy, j);
-        fe_sub(s, y, jy);
-        fe_mul(s, s, inv);
-        fe_sqr(rx, s);
-        fe_sub(rx, rx, jx);
-        fe_sub(rx, rx, x);
-        fe_sub(ry, x, rx);
-        fe_mul(ry, ry, s);
-        fe_sub(ry, ry, y);
-        st[(g * CHUNKS + 0) * T] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
-        st[(g * CHUNKS + 1) * T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
-        st[(g * CHUNKS + 2) * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
-        st[(g * CHUNKS + 3) * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
-        u32 d[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
-        d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
-        st[(g * CHUNKS + 4) * T] = make_uint4(d[0], d[1], d[2], d[3]);
-        if (((rx[7] & mhi) | (rx[6] & mlo)) == 0u) {
-          const u64 kidx = (u64)tile * (T * G) + (u64)g * T + (u64)t;
-          if (kidx < p.nKangaroos) {
-            const u32 pos = atomicAdd(p.out, 1u);
-            if (pos < p.maxFound) {
-              u32* o = p.out + 1 + (size_t)pos * 14;
-#pragma unroll
-              for (int w = 0; w < 8; w++) o[w] = rx[w];
-              o[8] = d[0]; o[9] = d[1]; o[10] = d[2]; o[11] = d[3];
-              o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
-            }
-          }
-        }
-        if (!last) {
-          lds_jp(jx, jpx, rx[0] & 31u);
-          fe_sub(dx, rx, jx);
-          if (i == 0) {
-            pr[(g * 2) * T] = make_uint4(1, 0, 0, 0); pr[(g * 2 + 1) * T] = make_uint4(0, 0, 0, 0);
-            fe_copy(P, dx);
-          } else {
-            pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
-            fe_mul(P, P, dx);
-          }
-        }
-        cur = nxt;
+      for (int i = 0; i < G; i += 2) {
+        const int ga = g0 + dg * i, gb = ga + dg;
+        stream_load<T>(B, st, pr, gb);
+        stream_body<T, G>(A, st, pr, jpx, jpy, jd, I, P, ga, i, last, p, mlo, mhi, kbase);
+        if (i + 2 < G) stream_load<T>(A, st, pr, gb + dg);
+        stream_body<T, G>(B, st, pr, jpx, jpy, jd, I, P, gb, i + 1, last, p, mlo, mhi, kbase);
       }
       backward ^= 1;
     }
@@ -419,14 +431,17 @@ __global__ void test_field_kernel(int op, int n, const u32* a, const u32* b, u32
 __global__ void bench_raw_kernel(int kind, int iters, u32* sink) {
   const u32 seed = blockIdx.x * blockDim.x + threadIdx.x + 1u;
   if (kind == 0) {
+    // 8 independent accumulators, multiplier changes every iteration so nothing can be hoisted:
+    // measures the IMAD.WIDE.U32 issue rate of the fmaheavy pipe (the multiplier roofline of this engine).
     u64 acc[8];
+    u32 x[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = seed * (k + 3u);
-    const u32 m0 = seed | 1u, m1 = seed * 7u + 5u;
+    for (int k = 0; k < 8; k++) { acc[k] = seed * (k + 3u); x[k] = seed + k * 1315423911u; }
+    u32 m1 = seed * 7u + 5u;
     for (int it = 0; it < iters; it++) {
+      m1 = m1 * 0x9E3779B1u + 12345u;
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(m0 + k), "r"(m1));
+      for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x[k]), "r"(m1));
     }
     u64 s = 0;
 #pragma unroll

@@ -1,0 +1,42 @@
+"""-m gpu: the reference's UNMODIFIED host program (main/Kangaroo/Check/HashTable/SECPK1, compiled from
+/root/reference by kangaroo_b200/csrc/build_dropin.sh) linked against the B200 engine through the GPUEngine shim.
+  * `-check`  = the reference's own parity test, Check.cpp:467-621 (GPU vs CPU after NB_RUN jumps + DP set)
+  * in56 / in64 = end-to-end solves with published answers (README.md:146-147, 194-195)
+The binary is built in the build container (the reference sources do not exist on the GPU box) and travels."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "kangaroo_b200")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def run(args, timeout=600):
+    if not os.path.exists(BIN):
+        pytest.skip("build/kangaroo_b200 not built (needs the reference sources at build time)")
+    p = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    return p.stdout + p.stderr
+
+
+def test_reference_check_gpu_vs_cpu():
+    out = run(["-gpu", "-check", "-g", "8,128"])       # 131072 kangaroos -> ~32k DPs at dp=8 (< 65536 buffer)
+    assert "CPU/GPU ok" in out, out[-3000:]
+    assert "DP Mismatch" not in out and "not ok" not in out
+
+
+def test_reference_check_odd_grid():
+    out = run(["-gpu", "-check", "-g", "3,32"])
+    assert "CPU/GPU ok" in out, out[-3000:]
+
+
+def test_solve_in56():
+    out = run(["-t", "0", "-gpu", "-g", "16,128", os.path.join(GOLD, "in56.txt")])
+    assert "CD612C0F05F3DA03" in out.upper().replace(" ", ""), out[-2000:]
+
+
+def test_solve_in64():
+    out = run(["-t", "0", "-gpu", "-g", "64,128", os.path.join(GOLD, "in64.txt")], timeout=900)
+    assert "5B3F38AF935A3640D158E871CE6E9666DB862636383386EE510F18CCC3BD72EB" in out.upper(), out[-2000:]
