@@ -111,17 +111,22 @@ def load_in80_table():
 
 
 def build_herd(eng, case, rank):
-    """Synthetic herd of valid walkers: the fixture's reference-generated start rows tiled over the grid, then
-    decorrelated ON THE DEVICE by giving every 128-row replica a different number of warm-up jumps."""
+    """Synthetic herd shaped like Kangaroo::CreateHerd (Kangaroo.cpp:670-738): every kangaroo gets its own uniform
+    random distance in the 2^80 range (numpy PCG64, seeded per rank), wild ones shifted by -width/2 (mod n) and started
+    at key + d*G.  The point arithmetic runs on the device (kgx_create_herd), so all 4.85 M walkers are distinct valid
+    curve points; no part of the oracle is involved."""
     import numpy as np
-    from tests.golden_util import arrays
     n = eng.nbKangaroo
-    sx, sy, sd = arrays(case["start"])
-    rows = sx.shape[0]
-    idx = (np.arange(n) + rank * 17) % rows
-    d = np.zeros((n, 2), dtype=np.uint64)
-    d[:, 0] = sd[idx, 0]; d[:, 1] = sd[idx, 1]
-    eng.SetKangaroosRaw(sx[idx], sy[idx], d)
+    rng = np.random.Generator(np.random.PCG64(1234 + rank))
+    lo = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    hi = rng.integers(0, 1 << 16, size=n, dtype=np.uint64)          # 64 + 16 = 80-bit distances
+    order = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    wdiv2 = case["width_div2"]
+    d = [int(lo[i]) | (int(hi[i]) << 64) for i in range(n)]
+    for i in range(1, n, 2):
+        d[i] = (d[i] - wdiv2) % order
+    eng.SetWildOffset(wdiv2)
+    eng.CreateHerd(d, case["key"])
 
 
 def main():
@@ -182,7 +187,6 @@ def main():
     n = eng.nbKangaroo
     dp_mask = (~((1 << (64 - args.dp)) - 1)) & 0xFFFFFFFFFFFFFFFF if args.dp else 0
     eng.SetParams(dp_mask, *case["table"])
-    eng.SetWildOffset(0)
     build_herd(eng, case, rank)
 
     from kangaroo_b200.dist import DPGather

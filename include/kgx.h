@@ -59,6 +59,11 @@ int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint
 int kgx_download(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d);
 int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t py[4], const uint64_t d[2]);
 
+/* --- herd creation on the device (replaces the CPU side of Kangaroo::CreateHerd, Kangaroo.cpp:670-738):
+ *     kangaroo i starts at scalars[i]*G, plus `key` when (i + first_type) is odd (wild).  scalars: n x 4 limbs (mod the
+ *     group order), d128: n x 2 limbs stored as the (biased) distances. --- */
+int kgx_create_herd(kgx_engine* e, const uint64_t* scalars, const uint64_t* d128, const uint64_t keyx[4], const uint64_t keyy[4], int first_type);
+
 /* --- GPUEngine::callKernel (GPUEngine.cu:540-557): zero the DP count, start NB_RUN jumps, asynchronous --- */
 int kgx_launch_async(kgx_engine* e);
 /* First half of GPUEngine::Launch (GPUEngine.cu:607-675): wait for the in-flight launch (sleeping unless

@@ -12,6 +12,7 @@
 #include <unistd.h>
 #include "../../include/kgx.h"
 #include "kgx_kernel.cuh"
+#include "kgx_herd.cuh"
 
 using namespace kgx;
 
@@ -29,6 +30,7 @@ struct kgx_engine {
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
   u32* slabPinned = nullptr;
   u32* jtab = nullptr;
+  u32* herdTab = nullptr;    // 256 x 16 words: 2^i * G (built on first kgx_create_herd)
   uint4 *stgX = nullptr, *stgY = nullptr, *stgD = nullptr;   // device staging (AoS, kIdx order)
   u64 dpMask = 0;
   bool haveParams = false, inflight = false;
@@ -100,7 +102,7 @@ void kgx_destroy(kgx_engine* e) {
   if (!e) return;
   cudaSetDevice(e->dev);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->state); cudaFree(e->pre); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
+  cudaFree(e->herdTab); cudaFree(e->state); cudaFree(e->pre); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
   cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
   if (e->slabPinned) cudaFreeHost(e->slabPinned);
   for (int i = 0; i < 2; i++) { if (e->evStart[i]) cudaEventDestroy(e->evStart[i]); if (e->evStop[i]) cudaEventDestroy(e->evStop[i]); }
@@ -270,6 +272,40 @@ int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t
   e->launches++;
   CK(e, cudaGetLastError());
   // padding slots replicate kangaroo (s % n): keep them walking their stale copy -- harmless, their DPs are dropped.
+  return 0;
+}
+
+// Kangaroo::CreateHerd on the device (Kangaroo.cpp:670-738): positions d*G (tame) / key + d*G (wild) for all n
+// kangaroos straight into the engine state.  scalars: n x 4 limbs (d mod group order, exactly what the reference
+// feeds ComputePublicKeys); d128: n x 2 limbs (the biased distances to store); key: x[4], y[4].
+int kgx_create_herd(kgx_engine* e, const uint64_t* scalars, const uint64_t* d128, const uint64_t keyx[4], const uint64_t keyy[4], int first_type) {
+  CK(e, cudaSetDevice(e->dev));
+  if (!e->herdTab) {
+    CK(e, cudaMalloc(&e->herdTab, 256 * 16 * 4));
+    herd_table_kernel<<<1, 32, 0, e->stream>>>(e->herdTab);
+    e->launches++;
+    CK(e, cudaGetLastError());
+  }
+  if (ensure_staging(e)) return -1;
+  u32 *dScal = nullptr, *dKey = nullptr;
+  CK(e, cudaMalloc(&dScal, e->n * 32));
+  CK(e, cudaMalloc(&dKey, 64));
+  uint64_t key[8];
+  memcpy(key, keyx, 32); memcpy(key + 4, keyy, 32);
+  CK(e, cudaMemcpyAsync(dScal, scalars, e->n * 32, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(dKey, key, 64, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->stgD, d128, e->n * 16, cudaMemcpyHostToDevice, e->stream));
+  herd_kernel<<<(u32)((e->n + 127) / 128), 128, 0, e->stream>>>(e->herdTab, dScal, dKey, first_type, e->n,
+                                                               reinterpret_cast<u32*>(e->stgX), reinterpret_cast<u32*>(e->stgY));
+  e->launches++;
+  CK(e, cudaGetLastError());
+  u32 blocks = (u32)((e->nPadded + 255) / 256);
+  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  CK(e, cudaStreamSynchronize(e->stream));
+  cudaFree(dScal); cudaFree(dKey);
+  free_staging(e);
   return 0;
 }
 

@@ -177,6 +177,20 @@ class GPUEngine:
         ad = _limbs(self._bias([d], kIdx), 2)
         self._ck(self._lib.kgx_patch(self._h, ctypes.c_uint64(kIdx), _p(ax), _p(ay), _p(ad)), "SetKangaroo")
 
+    def CreateHerd(self, d, key):
+        """Kangaroo::CreateHerd (Kangaroo.cpp:670-738) with the point arithmetic on the device: kangaroo i starts at
+        d[i]*G (tame, even kIdx) or key + d[i]*G (wild, odd kIdx) -- the reference always builds the GPU herd with
+        firstType = TAME (Kangaroo.cpp:540-545); d are ints mod n (wild ones already shifted by -rangeWidth/2 as the
+        reference does).  Distances are stored biased like SetKangaroos."""
+        firstType = TAME
+        n = self.nbKangaroo
+        dl = _ints(d) if isinstance(d, np.ndarray) else list(d)
+        assert len(dl) == n
+        sc = _limbs(dl, 4)
+        ad = _limbs(self._bias(dl, firstType), 2)
+        kx, ky = _limbs([key[0]], 4), _limbs([key[1]], 4)
+        self._ck(self._lib.kgx_create_herd(self._h, _p(sc), _p(ad), _p(kx), _p(ky), int(firstType)), "CreateHerd")
+
     def callKernel(self):
         """GPUEngine.cu:540-557."""
         return self._lib.kgx_launch_async(self._h) == 0
