@@ -116,17 +116,12 @@ def build_herd(eng, case, rank):
     at key + d*G.  The point arithmetic runs on the device (kgx_create_herd), so all 4.85 M walkers are distinct valid
     curve points; no part of the oracle is involved."""
     import numpy as np
-    n = eng.nbKangaroo
+    from kangaroo_b200 import random_herd_arrays
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
-    lo = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
-    hi = rng.integers(0, 1 << 16, size=n, dtype=np.uint64)          # 64 + 16 = 80-bit distances
-    order = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
     wdiv2 = case["width_div2"]
-    d = [int(lo[i]) | (int(hi[i]) << 64) for i in range(n)]
-    for i in range(1, n, 2):
-        d[i] = (d[i] - wdiv2) % order
     eng.SetWildOffset(wdiv2)
-    eng.CreateHerd(d, case["key"])
+    sc, d128 = random_herd_arrays(eng.nbKangaroo, 80, wdiv2, rng)
+    eng.CreateHerdRaw(sc, d128, case["key"])
 
 
 def main():

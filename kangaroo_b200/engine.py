@@ -191,6 +191,15 @@ class GPUEngine:
         kx, ky = _limbs([key[0]], 4), _limbs([key[1]], 4)
         self._ck(self._lib.kgx_create_herd(self._h, _p(sc), _p(ad), _p(kx), _p(ky), int(firstType)), "CreateHerd")
 
+    def CreateHerdRaw(self, scalars, d128, key):
+        """CreateHerd from limb arrays: scalars (n,4) uint64 = d mod n (what the points are computed from),
+        d128 (n,2) uint64 = the biased distances to store."""
+        n = self.nbKangaroo
+        sc, ad = _limbs(scalars, 4), _limbs(d128, 2)
+        assert sc.shape[0] == n and ad.shape[0] == n
+        kx, ky = _limbs([key[0]], 4), _limbs([key[1]], 4)
+        self._ck(self._lib.kgx_create_herd(self._h, _p(sc), _p(ad), _p(kx), _p(ky), TAME), "CreateHerd")
+
     def callKernel(self):
         """GPUEngine.cu:540-557."""
         return self._lib.kgx_launch_async(self._h) == 0
@@ -234,3 +243,42 @@ class GPUEngine:
 
     def dp_slab_device_ptr(self):
         return int(self._lib.kgx_dp_slab_device(self._h))
+
+
+def random_herd_arrays(n, range_power, wdiv2, rng):
+    """Vectorised distances for Kangaroo::CreateHerd (Kangaroo.cpp:696-704): v uniform in [0, 2^rangePower) for every
+    kangaroo; tame scalar = v, wild scalar = v - width/2 (mod n).  Returns (scalars (n,4), d128 (n,2)) uint64 where d128
+    is the device distance when wildOffset == width/2 (then wild bias + shift cancel: stored distance = v)."""
+    assert range_power <= 128
+    v = np.zeros((n, 4), dtype=np.uint64)
+    for k in range((range_power + 63) // 64):
+        v[:, k] = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    top = range_power % 64
+    if top:
+        v[:, (range_power - 1) // 64] &= np.uint64((1 << top) - 1)
+    d128 = np.ascontiguousarray(v[:, :2])
+    sc = v.copy()
+    w = [(wdiv2 >> (64 * k)) & _M64 for k in range(4)]
+    odd = np.arange(n) % 2 == WILD
+    borrow = np.zeros(n, dtype=np.uint64)
+    for k in range(4):                                   # sc[odd] -= wdiv2 (4-limb subtract with borrow)
+        a = sc[:, k]
+        sub = np.uint64(w[k])
+        t = a - sub
+        b1 = (a < sub).astype(np.uint64)
+        t2 = t - borrow
+        b2 = (t < borrow).astype(np.uint64)
+        sc[:, k] = np.where(odd, t2, a)
+        borrow = np.where(odd, b1 | b2, 0).astype(np.uint64)
+    neg = borrow.astype(bool)                            # went negative: add the group order back
+    carry = np.zeros(n, dtype=np.uint64)
+    for k in range(4):
+        a = sc[:, k]
+        addv = np.uint64((ORDER >> (64 * k)) & _M64)
+        t = a + addv
+        c1 = (t < a).astype(np.uint64)
+        t2 = t + carry
+        c2 = (t2 < t).astype(np.uint64)
+        sc[:, k] = np.where(neg, t2, a)
+        carry = np.where(neg, c1 | c2, 0).astype(np.uint64)
+    return sc, d128
