@@ -266,19 +266,33 @@ __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) 
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
 
-// One kangaroo of the fused pass (see the file header): back-substitute, jump, emit, start the next chain.
-template <int T, int G>
-__device__ __forceinline__ void stream_body(const KangLoad& cur, uint4* st, uint4* pr, const u32* jpx, const u32* jpy,
-                                            const u32* jd, u32* I, u32* P, const int g, const int i, const bool last,
-                                            const LaunchParams& p, const u32 mlo, const u32 mhi, const u64 kbase) {
-  u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8];
+// DP record append (GPUCompute.h:96-105, GPUMath.h:173-188): rare path, kept out of line so the jump loop stays one
+// basic block and ptxas can interleave the two kangaroos of an unrolled pair.
+__device__ __noinline__ void emit_dp(const LaunchParams& p, const u32* rx, const u32* d, u64 kidx) {
+  if (kidx >= p.nKangaroos) return;                    // padding slot
+  const u32 pos = atomicAdd(p.out, 1u);
+  if (pos >= p.maxFound) return;                       // GPUEngine.cu:641-648: counted, not stored
+  u32* o = p.out + 1 + (size_t)pos * 14;
+#pragma unroll
+  for (int w = 0; w < 8; w++) o[w] = rx[w];
+  o[8] = d[0]; o[9] = d[1]; o[10] = d[2]; o[11] = d[3];
+  o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
+}
+
+// One kangaroo of the fused pass (see the file header): back-substitute, jump, start the next chain.  Branch-free:
+// returns whether the new point is distinguished, leaving x' in rx[] and the new distance in d[] for emit_dp.
+template <int T>
+__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* st, uint4* pr, const u32* jpx, const u32* jpy,
+                                            const u32* jd, u32* I, u32* P, const int g, const u32 mlo, const u32 mhi,
+                                            u32* rx, u32* d) {
+  u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], ry[8];
   unpack8(x, cur.x0, cur.x1);
   unpack8(inv, cur.p0, cur.p1);
   const u32 j = x[0] & 31u;
   lds_jp(jx, jpx, j);
   fe_sub(dx, x, jx);
   fe_mul(inv, inv, I);                     // 1/dx
-  if (i != G - 1) fe_mul(I, I, dx);        // strip this dx from the running inverse
+  fe_mul(I, I, dx);                        // strip this dx from the running inverse (unused after the last one)
   unpack8(y, cur.y0, cur.y1);
   lds_jp(jy, jpy, j);
   fe_sub(s, y, jy);
@@ -293,33 +307,16 @@ __device__ __forceinline__ void stream_body(const KangLoad& cur, uint4* st, uint
   st[(g * CHUNKS + 1) * T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
   st[(g * CHUNKS + 2) * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
   st[(g * CHUNKS + 3) * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
-  u32 d[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
+  d[0] = cur.d.x; d[1] = cur.d.y; d[2] = cur.d.z; d[3] = cur.d.w;
   d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
   st[(g * CHUNKS + 4) * T] = make_uint4(d[0], d[1], d[2], d[3]);
-  if (((rx[7] & mhi) | (rx[6] & mlo)) == 0u) {          // GPUCompute.h:96
-    const u64 kidx = kbase + (u64)g * T;
-    if (kidx < p.nKangaroos) {
-      const u32 pos = atomicAdd(p.out, 1u);
-      if (pos < p.maxFound) {                           // GPUMath.h:173-188 record layout
-        u32* o = p.out + 1 + (size_t)pos * 14;
-#pragma unroll
-        for (int w = 0; w < 8; w++) o[w] = rx[w];
-        o[8] = d[0]; o[9] = d[1]; o[10] = d[2]; o[11] = d[3];
-        o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
-      }
-    }
-  }
-  if (!last) {                             // next jump's dx and prefix, accumulated in THIS order
-    lds_jp(jx, jpx, rx[0] & 31u);
-    fe_sub(dx, rx, jx);
-    if (i == 0) {
-      pr[(g * 2) * T] = make_uint4(1, 0, 0, 0); pr[(g * 2 + 1) * T] = make_uint4(0, 0, 0, 0);
-      fe_copy(P, dx);
-    } else {
-      pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
-      fe_mul(P, P, dx);
-    }
-  }
+  // next jump's dx and prefix product, accumulated in THIS order (P starts at 1 for the first kangaroo of a pass)
+  lds_jp(jx, jpx, rx[0] & 31u);
+  fe_sub(dx, rx, jx);
+  pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]);
+  pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
+  fe_mul(P, P, dx);
+  return ((rx[7] & mhi) | (rx[6] & mlo)) == 0u;          // GPUCompute.h:96
 }
 
 template <int T, int G, int CTAS>
@@ -339,6 +336,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
     uint4* pr = p.pre + (size_t)tile * (G * 2 * T) + t;
     const u64 kbase = (u64)tile * (T * G) + (u64)t;
     u32 P[8];
+    fe_set_one(P);
     {   // prologue: forward chain, pr[g] = product of the dx before g
       u32 x[8], jx[8], dx[8];
 #pragma unroll 1
@@ -346,30 +344,28 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
         unpack8(x, st[(g * CHUNKS + 0) * T], st[(g * CHUNKS + 1) * T]);
         lds_jp(jx, jpx, x[0] & 31u);
         fe_sub(dx, x, jx);
-        if (g == 0) {
-          pr[0] = make_uint4(1, 0, 0, 0); pr[T] = make_uint4(0, 0, 0, 0);
-          fe_copy(P, dx);
-        } else {
-          pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
-          fe_mul(P, P, dx);
-        }
+        pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
+        fe_mul(P, P, dx);
       }
     }
     int backward = 1;
     for (int run = 0; run < p.nRun; run++) {
       u32 I[8];
       fe_inv(I, P);                              // this thread's own group: 1 / (dx_0 ... dx_{G-1})
-      const bool last = (run == p.nRun - 1);
+      fe_set_one(P);
       const int g0 = backward ? (G - 1) : 0, dg = backward ? -1 : 1;
       KangLoad A, B;                              // ping-pong prefetch buffers (no register copies)
       stream_load<T>(A, st, pr, g0);
 #pragma unroll 1
       for (int i = 0; i < G; i += 2) {
         const int ga = g0 + dg * i, gb = ga + dg;
+        u32 rxa[8], da[4], rxb[8], db[4];
         stream_load<T>(B, st, pr, gb);
-        stream_body<T, G>(A, st, pr, jpx, jpy, jd, I, P, ga, i, last, p, mlo, mhi, kbase);
+        const bool ha = stream_body<T>(A, st, pr, jpx, jpy, jd, I, P, ga, mlo, mhi, rxa, da);
         if (i + 2 < G) stream_load<T>(A, st, pr, gb + dg);
-        stream_body<T, G>(B, st, pr, jpx, jpy, jd, I, P, gb, i + 1, last, p, mlo, mhi, kbase);
+        const bool hb = stream_body<T>(B, st, pr, jpx, jpy, jd, I, P, gb, mlo, mhi, rxb, db);
+        if (ha) emit_dp(p, rxa, da, kbase + (u64)ga * T);
+        if (hb) emit_dp(p, rxb, db, kbase + (u64)gb * T);
       }
       backward ^= 1;
     }
