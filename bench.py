@@ -242,6 +242,21 @@ def main():
     e2e_s = time.perf_counter() - t1
     sampler.stop_flag = True; sampler.join(timeout=2)
 
+    # ---- worst case for context: the whole herd round-trips through HOST memory every step (not how the reference
+    # interface is used -- SetKangaroos is a one-time upload -- but it bounds what a host-resident caller would see)
+    rt_steps, rt_s, rt_h2d, rt_d2h = 0, 0.0, 0, 0
+    if world == 1:
+        ax, ay, ad = eng.GetKangaroosRaw()
+        eng.sync()
+        t2 = time.perf_counter()
+        for _ in range(2):
+            eng.SetKangaroosRaw(ax, ay, ad)
+            eng.callKernel()
+            items = eng.Launch(relaunch=False)
+            ax, ay, ad = eng.GetKangaroosRaw()
+            rt_steps += 1; rt_h2d += n * 80; rt_d2h += n * 80 + 4 + len(items) * 56
+        rt_s = time.perf_counter() - t2
+
     t = torch.tensor([dev_s, wall, e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -298,6 +313,10 @@ def main():
                               "designed_gbs": kernel_value * 1e6 * DESIGN_BYTES_PER_JUMP.get(mode, 0) / 1e9}},
             kernel_mode=mode,
             gpu_launches=int(gpu_launches), clocks=clocks)
+        if rt_steps:
+            out["e2e_state_roundtrip"] = {"value": float(n) * NB_RUN * rt_steps / rt_s / 1e6, "unit": "MJump/s",
+                                          "h2d_bytes_per_step": rt_h2d / rt_steps, "d2h_bytes_per_step": rt_d2h / rt_steps,
+                                          "how": "SetKangaroos (pageable host -> device) + Launch + GetKangaroos every step"}
         if not args.no_cpu_baseline and world >= 1:
             base, _ = cpu_reference_run(12.0)
             out["cpu_baseline"] = base

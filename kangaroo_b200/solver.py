@@ -174,6 +174,12 @@ def main(argv=None):
             else:
                 print("Key#%2d not found" % i); rc = 1
         s.eng.close()
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
     return rc
 
 
