@@ -78,6 +78,9 @@ int kgx_sync(kgx_engine* e);
 /* Device pointer to the DP slab of the most recently COMPLETED launch: [u32 count][max_found x 56 B]. */
 void*    kgx_dp_slab_device(kgx_engine* e);
 uint32_t kgx_max_found(kgx_engine* e);
+/* HashTable::Convert on the device (HashTable.cpp:75-100) for the most recently completed launch:
+ * *out = device pointer to [u32 count][count x 40-byte DP {u32 kIdx; u32 h; u128 x; u128 tagged d}] (Kangaroo.h:94-101). */
+int      kgx_convert_dps(kgx_engine* e, const uint64_t wild_offset[2], void** out);
 /* Milliseconds the last completed launch spent on the device (CUDA events on the engine's stream). */
 float    kgx_last_launch_ms(kgx_engine* e);
 /* Jumps per launch override for tests (default KGX_NB_RUN). */

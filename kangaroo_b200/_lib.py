@@ -38,6 +38,7 @@ _SIGS = {
                                    ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_int]),
     "kgx_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "kgx_dp_slab_device": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "kgx_convert_dps": (ctypes.c_int, [ctypes.c_void_p, _u64p, ctypes.POINTER(ctypes.c_void_p)]),
     "kgx_max_found": (ctypes.c_uint32, [ctypes.c_void_p]),
     "kgx_last_launch_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "kgx_set_jumps_per_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

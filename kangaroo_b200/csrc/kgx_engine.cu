@@ -29,6 +29,7 @@ struct kgx_engine {
   bool streamMode = false;
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
   u32* slabPinned = nullptr;
+  u32* dp40 = nullptr;       // [count][maxFound x 10 words]: converted records of the last completed launch
   u32* jtab = nullptr;
   u32* herdTab = nullptr;    // 256 x 16 words: 2^i * G (built on first kgx_create_herd)
   uint4 *stgX = nullptr, *stgY = nullptr, *stgD = nullptr;   // device staging (AoS, kIdx order)
@@ -102,7 +103,7 @@ void kgx_destroy(kgx_engine* e) {
   if (!e) return;
   cudaSetDevice(e->dev);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->herdTab); cudaFree(e->state); cudaFree(e->pre); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
+  cudaFree(e->dp40); cudaFree(e->herdTab); cudaFree(e->state); cudaFree(e->pre); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
   cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
   if (e->slabPinned) cudaFreeHost(e->slabPinned);
   for (int i = 0; i < 2; i++) { if (e->evStart[i]) cudaEventDestroy(e->evStart[i]); if (e->evStop[i]) cudaEventDestroy(e->evStop[i]); }
@@ -115,6 +116,7 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
   kgx_engine* e = new kgx_engine();
   auto fail = [&](const char* what, cudaError_t s) -> kgx_engine* {
     snprintf(g_create_err, sizeof g_create_err, "kgx_create: %s: %s", what, cudaGetErrorString(s));
+    cudaGetLastError();   // do not leave a sticky error behind for the next engine of this process
     kgx_destroy(e);
     return nullptr;
   };
@@ -377,6 +379,20 @@ int kgx_sync(kgx_engine* e) {
     CK(e, cudaEventElapsedTime(&e->lastMs, e->evStart[e->cur], e->evStop[e->cur]));
     e->inflight = false; e->done = e->cur;
   }
+  return 0;
+}
+
+// HashTable::Convert on the device for the most recently completed launch.  wild_offset: 2 limbs.
+// Returns the device pointer of [u32 count][count x 40-byte DP records] through *out (valid until the next call).
+int kgx_convert_dps(kgx_engine* e, const uint64_t wild_offset[2], void** out) {
+  CK(e, cudaSetDevice(e->dev));
+  if (!e->dp40) CK(e, cudaMalloc(&e->dp40, (size_t)e->maxFound * 40 + 4));
+  const int sidx = e->done >= 0 ? e->done : e->cur;
+  dp_convert_kernel<<<64, 256, 0, e->copyStream>>>(e->slab[sidx], e->dp40, e->maxFound, wild_offset[0], wild_offset[1]);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  CK(e, cudaStreamSynchronize(e->copyStream));
+  *out = e->dp40;
   return 0;
 }
 

@@ -54,16 +54,19 @@ __device__ __forceinline__ void kgx_fold(u32* r, u32* w) {
       "addc.u32    %8, %17, 0;"
       : "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "=&r"(e[9])
       : "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]));
-  // second fold: top = e8 + e9*2^32 ; V = top*(2^32+c) = e8*c + (e8 + e9*c)*2^32 + e9*2^64 ; r = R1[0..7] + V (carry dropped)
+  // second fold: top = e8 + e9*2^32 (e9 <= 2) ; V = top*(2^32+c) = e8*c + (e8 + e9*c)*2^32 + e9*2^64 ; r = R1[0..7] + V,
+  // last carry dropped.  One wide multiply (e8*c) + one small 32-bit multiply (e9*c < 2^12).
   u32 v0, v1, v2;
   asm("{\n\t"
-      ".reg .u32 ulo, uhi;\n\t"
-      "mul.lo.u32     %0, %3, %5;\n\t"
-      "mul.hi.u32     %1, %3, %5;\n\t"
-      "mad.lo.cc.u32  ulo, %4, %5, %3;\n\t"
-      "addc.u32       uhi, 0, 0;\n\t"
-      "add.cc.u32     %1, %1, ulo;\n\t"
-      "addc.u32       %2, %4, uhi;\n\t"
+      ".reg .u32 q;\n\t"
+      ".reg .u64 pw;\n\t"
+      "mul.wide.u32   pw, %3, %5;\n\t"
+      "mov.b64        {%0, %1}, pw;\n\t"
+      "mul.lo.u32     q, %4, %5;\n\t"
+      "add.cc.u32     %1, %1, %3;\n\t"
+      "addc.u32       %2, %4, 0;\n\t"
+      "add.cc.u32     %1, %1, q;\n\t"
+      "addc.u32       %2, %2, 0;\n\t"
       "}"
       : "=&r"(v0), "=&r"(v1), "=&r"(v2)
       : "r"(e[8]), "r"(e[9]), "r"(c));

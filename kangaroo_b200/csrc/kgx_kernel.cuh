@@ -408,6 +408,36 @@ __global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K) {
   if (threadIdx.x < CHUNKS) dst[(g * CHUNKS + threadIdx.x) * T + t] = a.c[threadIdx.x];
 }
 
+// ---- device-side HashTable::Convert (HashTable.cpp:75-100) -------------------------------------------
+// 56-byte engine record {x[8 words], biased d[4 words], kIdx[2 words]} -> the reference's 40-byte wire/disk record
+// DP {u32 kIdx; u32 h; int128 x; int128 d} (Kangaroo.h:94-101): h = x.bits64[2] & 0x3FFFF, x = 128 LSBs,
+// d = |distance| (126 bits) | sign << 127 | type << 126 with distance = biased d - wildOffset for wild kangaroos
+// (GPUEngine.cu:672) taken as a signed value (the reference forms it mod n and tests the top bit).
+__global__ void dp_convert_kernel(const u32* __restrict__ slab, u32* __restrict__ out40, u32 maxFound, u64 wo0, u64 wo1) {
+  const u32 cnt = min(slab[0], maxFound);
+  if (blockIdx.x == 0 && threadIdx.x == 0) out40[0] = cnt;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const u32* r = slab + 1 + (size_t)i * 14;
+    u32* o = out40 + 1 + (size_t)i * 10;
+    const u64 kidx = (u64)r[12] | ((u64)r[13] << 32);
+    const u32 type = (u32)(kidx & 1ull);
+    u64 d0 = (u64)r[8] | ((u64)r[9] << 32), d1 = (u64)r[10] | ((u64)r[11] << 32);
+    u64 sign = 0;
+    if (type) {                                   // wild: subtract the offset, keep magnitude + sign
+      const u64 b0 = d0 < wo0;
+      u64 t0 = d0 - wo0, t1 = d1 - wo1 - b0;
+      const bool neg = (d1 < wo1) || (d1 == wo1 && d0 < wo0);
+      if (neg) { t0 = ~t0 + 1; t1 = ~t1 + (t0 == 0); sign = 1ull << 63; }
+      d0 = t0; d1 = t1;
+    }
+    d1 = (d1 & 0x3FFFFFFFFFFFFFFFull) | sign | ((u64)type << 62);
+    o[0] = (u32)kidx;
+    o[1] = r[4] & 0x3FFFFu;                       // x.bits64[2] low word & HASH_MASK
+    o[2] = r[0]; o[3] = r[1]; o[4] = r[2]; o[5] = r[3];
+    o[6] = (u32)d0; o[7] = (u32)(d0 >> 32); o[8] = (u32)d1; o[9] = (u32)(d1 >> 32);
+  }
+}
+
 // ---- unit-test / microbench kernels ------------------------------------------------------------------
 __global__ void test_field_kernel(int op, int n, const u32* a, const u32* b, u32* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

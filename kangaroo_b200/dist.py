@@ -13,6 +13,7 @@ The payload is read straight from the engine's device DP slab (no host bounce); 
 launch is already running on the engine's own stream while the gather proceeds on torch's stream.
 """
 ITEM_BYTES = 56
+DP40_BYTES = 40
 ROUND = 256
 
 
@@ -24,14 +25,18 @@ class SlabView:
 
 
 class DPGather:
-    def __init__(self, engine, dist, rank, world, torch, device=None, slab_fn=None, max_found=None):
+    def __init__(self, engine, dist, rank, world, torch, device=None, slab_fn=None, max_found=None, wire="item56"):
         """engine: kangaroo_b200.GPUEngine (or None with slab_fn for the CPU/gloo tests).
         slab_fn() -> uint8 tensor [4 + max_found*56] of the most recently completed launch."""
         self.eng, self.dist, self.rank, self.world, self.torch = engine, dist, rank, world, torch
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.max_found = max_found if max_found is not None else engine.maxFound
         self._views = {}
-        self._slab_fn = slab_fn if slab_fn is not None else self._engine_slab
+        # wire = "item56": raw engine records; "dp40": the reference's 40-byte DP records, converted on the device
+        # (HashTable::Convert, SURVEY 8f/f1) -- 29 % less gather traffic and ready for HashTable::Add(h, x, d)
+        self.rec = ITEM_BYTES if wire == "item56" else DP40_BYTES
+        self.wire = wire
+        self._slab_fn = slab_fn if slab_fn is not None else (self._engine_slab if wire == "item56" else self._engine_dp40)
         self.total_gathered = 0
         self.last = None
 
@@ -42,6 +47,14 @@ class DPGather:
             nbytes = 4 + self.max_found * ITEM_BYTES
             v = self.torch.as_tensor(SlabView(ptr, nbytes), device=self.device)
             self._views[ptr] = v
+        return v
+
+    def _engine_dp40(self):
+        ptr = self.eng.convert_dps_device_ptr()
+        v = self._views.get(("dp40", ptr))
+        if v is None:
+            v = self.torch.as_tensor(SlabView(ptr, 4 + self.max_found * DP40_BYTES), device=self.device)
+            self._views[("dp40", ptr)] = v
         return v
 
     def step(self, n_found):
@@ -56,11 +69,11 @@ class DPGather:
         cap = max(ROUND, (max(counts_h) + ROUND - 1) // ROUND * ROUND)
         cap = min(cap, self.max_found)
         slab = self._slab_fn()
-        local = slab[4:4 + cap * ITEM_BYTES]
+        local = slab[4:4 + cap * self.rec]
         if self.rank == 0:
-            bufs = [torch.empty(cap * ITEM_BYTES, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+            bufs = [torch.empty(cap * self.rec, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
             dist.gather(local, bufs, dst=0)
-            out = [(r, bufs[r][:counts_h[r] * ITEM_BYTES]) for r in range(self.world)]
+            out = [(r, bufs[r][:counts_h[r] * self.rec]) for r in range(self.world)]
         else:
             dist.gather(local, None, dst=0)
             out = None
@@ -80,4 +93,19 @@ def decode_records(buf):
         d = int.from_bytes(b[o + 32:o + 48], "little")
         k = int.from_bytes(b[o + 48:o + 56], "little")
         out.append((x, d, k))
+    return out
+
+
+def decode_dp40(buf):
+    """40-byte DP records -> list of (kIdx32, h, x128, dist (signed int), type): HashTable::CalcDistAndType (HashTable.cpp:249-260)."""
+    b = bytes(buf.cpu().numpy().tobytes()) if hasattr(buf, "cpu") else bytes(buf)
+    out = []
+    for o in range(0, len(b), DP40_BYTES):
+        kidx = int.from_bytes(b[o:o + 4], "little")
+        h = int.from_bytes(b[o + 4:o + 8], "little")
+        x = int.from_bytes(b[o + 8:o + 24], "little")
+        d = int.from_bytes(b[o + 24:o + 40], "little")
+        ktype = (d >> 126) & 1
+        mag = d & ((1 << 126) - 1)
+        out.append((kidx, h, x, -mag if d >> 127 else mag, ktype))
     return out

@@ -241,6 +241,14 @@ class GPUEngine:
     def kernel_launches(self):
         return int(self._lib.kgx_kernel_launches(self._h))
 
+    def convert_dps_device_ptr(self):
+        """HashTable::Convert on the device for the last completed launch -> device pointer of
+        [u32 count][40-byte DP records] (Kangaroo.h:94-101)."""
+        wo = _limbs([self.wildOffset & ((1 << 128) - 1)], 2)
+        out = ctypes.c_void_p(0)
+        self._ck(self._lib.kgx_convert_dps(self._h, _p(wo), ctypes.byref(out)), "convert_dps")
+        return int(out.value)
+
     def dp_slab_device_ptr(self):
         return int(self._lib.kgx_dp_slab_device(self._h))
 

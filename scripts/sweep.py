@@ -15,7 +15,7 @@ def main():
     cfgs = sys.argv[1:] or ["128,7", "128,5", "128,4", "96,6", "64,7", "64,6", "64,5", "64,4", "256,3", "32,8", "32,12"]
     case = [c for c in load_cases() if c["range_power"] == 80][0]
     sx, sy, sd = arrays(case["start"])
-    gx, gy = 296, 128
+    gx, gy = (int(v) for v in os.environ.get('KGX_SWEEP_GRID', '296,128').split(','))
     n = gx * gy * 128
     idx = np.arange(n) % sx.shape[0]
     ax, ay = sx[idx], sy[idx]
