@@ -255,12 +255,14 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
 // =====================================================================================================
 struct KangLoad { uint4 p0, p1, x0, x1, y0, y1, d; };
 
+// sg / pg point at this thread's column of kangaroo g: sg = st + g*CHUNKS*T, pg = pr + g*2*T (running pointers: the
+// hot loop does no index multiplications -- IMAD shares the binding pipe)
 template <int T>
-__device__ __forceinline__ void stream_load(KangLoad& k, const uint4* st, const uint4* pr, int g) {
-  k.p0 = pr[(g * 2 + 0) * T]; k.p1 = pr[(g * 2 + 1) * T];
-  k.x0 = st[(g * CHUNKS + 0) * T]; k.x1 = st[(g * CHUNKS + 1) * T];
-  k.y0 = st[(g * CHUNKS + 2) * T]; k.y1 = st[(g * CHUNKS + 3) * T];
-  k.d = st[(g * CHUNKS + 4) * T];
+__device__ __forceinline__ void stream_load(KangLoad& k, const uint4* sg, const uint4* pg) {
+  k.p0 = pg[0]; k.p1 = pg[T];
+  k.x0 = sg[0]; k.x1 = sg[T];
+  k.y0 = sg[2 * T]; k.y1 = sg[3 * T];
+  k.d = sg[4 * T];
 }
 __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) {
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
@@ -268,6 +270,8 @@ __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) 
 
 // DP record append (GPUCompute.h:96-105, GPUMath.h:173-188): rare path, kept out of line so the jump loop stays one
 // basic block and ptxas can interleave the two kangaroos of an unrolled pair.
+// (pointer arguments: the caller's rx/d arrays get a local-memory home that is written once per jump with three
+// STL.128; passing the 14 words by value instead costs 17 more registers and measured 2 % slower)
 __device__ __noinline__ void emit_dp(const LaunchParams& p, const u32* rx, const u32* d, u64 kidx) {
   if (kidx >= p.nKangaroos) return;                    // padding slot
   const u32 pos = atomicAdd(p.out, 1u);
@@ -282,8 +286,8 @@ __device__ __noinline__ void emit_dp(const LaunchParams& p, const u32* rx, const
 // One kangaroo of the fused pass (see the file header): back-substitute, jump, start the next chain.  Branch-free:
 // returns whether the new point is distinguished, leaving x' in rx[] and the new distance in d[] for emit_dp.
 template <int T>
-__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* st, uint4* pr, const u32* jpx, const u32* jpy,
-                                            const u32* jd, u32* I, u32* P, const int g, const u32 mlo, const u32 mhi,
+__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, const u32* jpx, const u32* jpy,
+                                            const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi,
                                             u32* rx, u32* d) {
   u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], ry[8];
   unpack8(x, cur.x0, cur.x1);
@@ -303,18 +307,18 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* st, uint
   fe_sub(ry, x, rx);
   fe_mul(ry, ry, s);
   fe_sub(ry, ry, y);                       // ry = s (x - rx) - y
-  st[(g * CHUNKS + 0) * T] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
-  st[(g * CHUNKS + 1) * T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
-  st[(g * CHUNKS + 2) * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
-  st[(g * CHUNKS + 3) * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
+  sg[0] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
+  sg[T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
+  sg[2 * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
+  sg[3 * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
   d[0] = cur.d.x; d[1] = cur.d.y; d[2] = cur.d.z; d[3] = cur.d.w;
   d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
-  st[(g * CHUNKS + 4) * T] = make_uint4(d[0], d[1], d[2], d[3]);
+  sg[4 * T] = make_uint4(d[0], d[1], d[2], d[3]);
   // next jump's dx and prefix product, accumulated in THIS order (P starts at 1 for the first kangaroo of a pass)
   lds_jp(jx, jpx, rx[0] & 31u);
   fe_sub(dx, rx, jx);
-  pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]);
-  pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
+  pg[0] = make_uint4(P[0], P[1], P[2], P[3]);
+  pg[T] = make_uint4(P[4], P[5], P[6], P[7]);
   fe_mul(P, P, dx);
   return ((rx[7] & mhi) | (rx[6] & mlo)) == 0u;          // GPUCompute.h:96
 }
@@ -353,19 +357,25 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
       u32 I[8];
       fe_inv(I, P);                              // this thread's own group: 1 / (dx_0 ... dx_{G-1})
       fe_set_one(P);
-      const int g0 = backward ? (G - 1) : 0, dg = backward ? -1 : 1;
+      const int g0 = backward ? (G - 1) : 0;
+      const ptrdiff_t ds = backward ? -(ptrdiff_t)(CHUNKS * T) : (ptrdiff_t)(CHUNKS * T);   // pointer steps per kangaroo
+      const ptrdiff_t dp = backward ? -(ptrdiff_t)(2 * T) : (ptrdiff_t)(2 * T);
+      const long long dk = backward ? -(long long)T : (long long)T;
+      uint4* sg = st + (size_t)g0 * (CHUNKS * T);
+      uint4* pg = pr + (size_t)g0 * (2 * T);
+      u64 kidx = kbase + (u64)g0 * T;
       KangLoad A, B;                              // ping-pong prefetch buffers (no register copies)
-      stream_load<T>(A, st, pr, g0);
+      stream_load<T>(A, sg, pg);
 #pragma unroll 1
       for (int i = 0; i < G; i += 2) {
-        const int ga = g0 + dg * i, gb = ga + dg;
         u32 rxa[8], da[4], rxb[8], db[4];
-        stream_load<T>(B, st, pr, gb);
-        const bool ha = stream_body<T>(A, st, pr, jpx, jpy, jd, I, P, ga, mlo, mhi, rxa, da);
-        if (i + 2 < G) stream_load<T>(A, st, pr, gb + dg);
-        const bool hb = stream_body<T>(B, st, pr, jpx, jpy, jd, I, P, gb, mlo, mhi, rxb, db);
-        if (ha) emit_dp(p, rxa, da, kbase + (u64)ga * T);
-        if (hb) emit_dp(p, rxb, db, kbase + (u64)gb * T);
+        stream_load<T>(B, sg + ds, pg + dp);
+        const bool ha = stream_body<T>(A, sg, pg, jpx, jpy, jd, I, P, mlo, mhi, rxa, da);
+        if (i + 2 < G) stream_load<T>(A, sg + 2 * ds, pg + 2 * dp);
+        const bool hb = stream_body<T>(B, sg + ds, pg + dp, jpx, jpy, jd, I, P, mlo, mhi, rxb, db);
+        if (ha) emit_dp(p, rxa, da, kidx);
+        if (hb) emit_dp(p, rxb, db, kidx + dk);
+        sg += 2 * ds; pg += 2 * dp; kidx += 2 * dk;
       }
       backward ^= 1;
     }
