@@ -225,18 +225,27 @@ def main():
     kernel_ms = kernel_ms[1:] + [eng.last_launch_ms()]
     dev_s = sum(kernel_ms) / 1e3
 
-    # ---- end-to-end leg through the reference-shaped API (host ITEM lists) ------------------------------
+    # ---- end-to-end leg through the C ABI with HOST buffers: kgx_collect(..., relaunch=1) is exactly the body of
+    # GPUEngine::Launch (GPUEngine.cu:607-679): wait for the kernel, start the next one, copy this launch's DP records
+    # device -> pinned staging -> the caller's host array of 56-byte items (what SolveKeyGPU then hashes).
+    from kangaroo_b200._lib import Item
+    host_items = (Item * max_found)()
     eng.callKernel()
+
+    def e2e_step():
+        rc = lib.kgx_collect(eng._h, host_items, max_found, ctypes.byref(nI), ctypes.byref(nF), 0, 1)
+        assert rc == 0, lib.kgx_last_error(eng._h)
+        if gather is not None:
+            gather.step(int(nF.value))
+        return int(nI.value)
+
     for _ in range(2):
-        eng.Launch()
+        e2e_step()
     barrier()
     t1 = time.perf_counter()
     d2h = 0
     for _ in range(steps):
-        items = eng.Launch()
-        d2h += 4 + len(items) * 56
-        if gather is not None:
-            gather.step(len(items))
+        d2h += 4 + e2e_step() * 56
     eng.sync()
     barrier()
     e2e_s = time.perf_counter() - t1
@@ -299,7 +308,7 @@ def main():
             kernel_only={"value": kernel_value, "unit": "MJump/s/GPU", "ms_per_launch": dev_s / steps * 1e3,
                          "how": "CUDA events on the engine stream around each jump_kernel launch"},
             e2e={"value": e2e_value, "unit": "MJump/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / max(steps, 1),
-                 "how": "GPUEngine.Launch loop: wait, DP records -> pinned host -> ITEM list, relaunch (Kangaroo.cpp:572-575)"},
+                 "how": "kgx_collect(relaunch=1) loop = GPUEngine::Launch through the C ABI: wait, relaunch, DP records device -> host item array (Kangaroo.cpp:572-575)"},
             roofline={"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s (32x32->64 multiply-adds)",
                       "frac": achieved / imad_peak, "traffic": traffic,
                       "algorithmic_imad_per_jump": ALGO_IMAD_PER_JUMP,

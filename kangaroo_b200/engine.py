@@ -215,13 +215,13 @@ class GPUEngine:
                   (n_found.value - self.maxFound))
             self.lostWarning = True
         self.lastFound = n_found.value
-        out = []
-        for i in range(n_items.value):
-            it = self._items[i]
-            x = it.x[0] | (it.x[1] << 64) | (it.x[2] << 128) | (it.x[3] << 192)
-            d = it.d[0] | (it.d[1] << 64)
-            out.append(ITEM(x, self._unbias(d, it.kidx), int(it.kidx)))
-        return out
+        k = n_items.value
+        if k == 0:
+            return []
+        # vectorised decode of the 56-byte records: 7 x u64 per item
+        raw = np.frombuffer(self._items, dtype=np.uint64, count=k * 7).reshape(k, 7)
+        xs = _ints(raw[:, 0:4]); ds = _ints(raw[:, 4:6]); ks = raw[:, 6].tolist()
+        return [ITEM(x, self._unbias(d, kk), int(kk)) for x, d, kk in zip(xs, ds, ks)]
 
     def callKernelAndWait(self):
         ok = self.callKernel()
