@@ -31,23 +31,17 @@ def main():
             best = r if best is None or r > best else best
         out[name + "_per_s"] = best
         print(name, "%.3e /s" % best, flush=True)
-    # jump kernel on a synthetic herd: every kangaroo = a valid point; use replicated walkers from the oracle-free path:
-    # G multiples are not available without the oracle, so use points generated on device by prior jumps: start all at G.
-    GX = 0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798
-    GY = 0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8
-    sys.path.insert(0, ROOT)
-    from oracle import kgo
-    orc = kgo.Oracle()
-    table = orc.create_jump_table(80)
+    # jump kernel on a synthetic herd built on the device (kgx_create_herd); jump table from the reference-generated fixture
+    from kangaroo_b200 import random_herd_arrays
+    from tests.golden_util import load_cases
+    case = [c for c in load_cases() if c["range_power"] == 80][0]
     for grid in ((296, 128), (74, 128), (16, 128)):
         n = grid[0] * grid[1] * 128
         eng = GPUEngine(grid[0], grid[1], 0, 1 << 20)
-        eng.SetParams(orc.dp_mask(16), *table)
-        base = 1024
-        from tests.gpu_util import cheap_herd
-        bx, by, bd = cheap_herd(orc, base, table, seed=5)
-        ax = np.tile(bx, (n // base, 1)); ay = np.tile(by, (n // base, 1)); ad = np.tile(bd[:, :2], (n // base, 1))
-        eng.SetKangaroosRaw(ax, ay, ad)
+        eng.SetParams(0xFFFF000000000000, *case["table"])
+        eng.SetWildOffset(case["width_div2"])
+        sc, d128 = random_herd_arrays(n, 80, case["width_div2"], np.random.Generator(np.random.PCG64(5)))
+        eng.CreateHerdRaw(sc, d128, case["key"])
         eng.callKernel()
         times = []
         for i in range(6):
