@@ -76,29 +76,54 @@ def cpu_reference_run(seconds_target):
 
 
 class ClockSampler(threading.Thread):
+    """One long-lived `nvidia-smi -lms 50` whose lines are stamped on arrival; result() keeps the samples that fell
+    inside the timed regions (the recipe's clocks line, B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, dev):
         super().__init__(daemon=True)
-        self.dev, self.samples, self.reasons, self.stop_flag, self.max_mhz = dev, [], set(), False, None
+        self.dev, self.rows, self.stop_flag, self.windows, self.proc = dev, [], False, [], None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), line.strip().split(",")))
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(n)
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
+        self.join(timeout=2)
 
     def result(self):
-        s = sorted(self.samples)
-        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(s))
+        mhz, reasons, max_mhz = [], set(), None
+        for t, f in self.rows:
+            try:
+                inside = any(a <= t <= b for a, b in self.windows)
+                max_mhz = float(f[1])
+                if inside:
+                    mhz.append(float(f[0]))
+                    for n, v in zip(self.NAMES, f[2:]):
+                        if "Active" in v and "Not" not in v:
+                            reasons.add(n)
+            except Exception:
+                continue
+        mhz.sort()
+        return dict(sm_mhz=(mhz[len(mhz) // 2] if mhz else None), sm_max_mhz=max_mhz, reasons=sorted(reasons), samples=len(mhz))
 
 
 def load_in80_table():
@@ -220,6 +245,7 @@ def main():
     eng.sync()
     barrier()
     wall = time.perf_counter() - t0
+    sampler.window(t0, t0 + wall)
     gpu_launches = eng.kernel_launches() - launches0
     # the K timed launches are exactly the K kernels completed inside the region: (K-1) collected + the one synced
     kernel_ms = kernel_ms[1:] + [eng.last_launch_ms()]
@@ -249,7 +275,8 @@ def main():
     eng.sync()
     barrier()
     e2e_s = time.perf_counter() - t1
-    sampler.stop_flag = True; sampler.join(timeout=2)
+    sampler.window(t1, t1 + e2e_s)
+    sampler.stop()
 
     # ---- worst case for context: the whole herd round-trips through HOST memory every step (not how the reference
     # interface is used -- SetKangaroos is a one-time upload -- but it bounds what a host-resident caller would see)
