@@ -151,10 +151,16 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
       snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream or resident"); delete e; return nullptr;
     }
     if (e->streamMode) {
-      int g = 128;
+      // kangaroos per thread: 128 (the reference's GPU_GRP_SIZE) when the herd fills two CTAs per SM with it; smaller
+      // herds get a smaller group so that the grid still covers the chip (one wave of 2 CTAs/SM), at the price of more
+      // inversions per jump.  KGX_STREAM_G overrides.
+      long long g = (long long)(e->n / ((u64)2 * prop.multiProcessorCount * 128));
+      if (g > 128) g = 128;
+      if (g < 2) g = 2;
+      g &= ~1LL;
       if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
-      if (g != 128 && g != 96 && g != 64 && g != 192 && g != 256) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_G must be 64, 96, 128, 192 or 256"); delete e; return nullptr; }
-      e->T = 128; e->K = g; e->smemBytes = 0; e->ctasPerSM = g == 64 ? 4 : (g == 96 ? 3 : 2);
+      if (g < 2 || g > 4096 || (g & 1)) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_G must be an even number in [2, 4096]"); delete e; return nullptr; }
+      e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = 2;
     }
   }
   const u64 TILE = (u64)e->T * e->K;
@@ -318,18 +324,12 @@ int kgx_launch_async(kgx_engine* e) {
   int sidx = e->cur ^ 1;
   LaunchParams p;
   p.state = e->state; p.jtab = e->jtab; p.out = e->slab[sidx]; p.dpMask = e->dpMask; p.nKangaroos = e->n;
-  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre;
+  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre; p.G = e->K;
   CK(e, cudaMemsetAsync(e->slab[sidx], 0, 4, e->stream));            // GPUEngine.cu:543
   CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
   u32 grid = (u32)(e->ctasPerSM * e->sms);
   if (grid > e->numTiles) grid = e->numTiles;
-  if (e->streamMode) {
-    if (e->K == 64) stream_kernel<128, 64, 4><<<grid, 128, 0, e->stream>>>(p);
-    else if (e->K == 96) stream_kernel<128, 96, 3><<<grid, 128, 0, e->stream>>>(p);
-    else if (e->K == 192) stream_kernel<128, 192, 2><<<grid, 128, 0, e->stream>>>(p);
-    else if (e->K == 256) stream_kernel<128, 256, 2><<<grid, 128, 0, e->stream>>>(p);
-    else stream_kernel<128, 128, 2><<<grid, 128, 0, e->stream>>>(p);
-  }
+  if (e->streamMode) stream_kernel<128, 2><<<grid, 128, 0, e->stream>>>(p);
   else g_cfgs[e->cfg].kern<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   e->launches++;
   CK(e, cudaGetLastError());

@@ -50,6 +50,7 @@ struct LaunchParams {
   u32 maxFound;
   int nRun;
   uint4* pre;            // streaming kernel only: prefix-product scratch [numTiles][G][2][T]
+  int G;                 // streaming kernel only: kangaroos per thread (even, chosen by the engine from the herd size)
   unsigned long long* prof;   // optional: [0]=sum serial cycles, [1]=sum modinv cycles, [2]=sum parallel cycles, [3]=tile-steps (warp 0 of every CTA)
 };
 
@@ -323,9 +324,9 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
   return ((rx[7] & mhi) | (rx[6] & mlo)) == 0u;          // GPUCompute.h:96
 }
 
-template <int T, int G, int CTAS>
+template <int T, int CTAS>
 __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
-  static_assert(G % 2 == 0, "the fused pass is unrolled by two");
+  const int G = p.G;     // even: the fused pass is unrolled by two
   __shared__ u32 sJ[JT_WORDS];
   const u32* jpx = sJ;
   const u32* jpy = sJ + 8 * 32;
