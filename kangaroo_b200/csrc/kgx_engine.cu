@@ -146,7 +146,10 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
   e->T = g_cfgs[e->cfg].T; e->K = g_cfgs[e->cfg].K; e->smemBytes = g_cfgs[e->cfg].smem; e->ctasPerSM = g_cfgs[e->cfg].ctas;
   {
     const char* mode = getenv("KGX_MODE");
-    e->streamMode = mode ? (strcmp(mode, "stream") == 0) : (KGX_DEFAULT_STREAM != 0);
+    // default: the streaming kernel for herds of a million kangaroos and more (it needs ~128 kangaroos per thread on
+    // every SM to amortise the per-thread inverse), the shared-memory tile kernel below that (its inverse is shared by a
+    // whole tile, so it keeps ~6.8 GJump/s down to ~300 k kangaroos) -- measured crossover, profiles/r1g_sweep.txt
+    e->streamMode = mode ? (strcmp(mode, "stream") == 0) : (KGX_DEFAULT_STREAM != 0 && e->n >= 1000000ull);
     if (mode && strcmp(mode, "stream") && strcmp(mode, "resident")) {
       snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream or resident"); delete e; return nullptr;
     }
