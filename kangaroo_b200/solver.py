@@ -16,7 +16,7 @@ import numpy as np
 
 from . import ecmath as ec
 from .engine import GPUEngine, NB_JUMP, NB_RUN, WILD, random_herd_arrays
-from .dist import DPGather, decode_records
+from .dist import DPGather, decode_records, decode_dp40
 
 ORDER = ec.N
 
@@ -49,7 +49,7 @@ def dp_mask(bits):
 
 
 class Solver:
-    def __init__(self, start, end, pub, dp_bits, grid=None, max_found=1 << 17, seed=None):
+    def __init__(self, start, end, pub, dp_bits, grid=None, max_found=1 << 17, seed=None, wire="item56"):
         import torch
         self.torch = torch
         self.rank = int(os.environ.get("RANK", "0"))
@@ -78,7 +78,8 @@ class Solver:
         rng = np.random.Generator(np.random.PCG64((seed if seed is not None else int(time.time())) * 1000 + self.rank))
         sc, d128 = random_herd_arrays(n, self.range_power, self.wdiv2, rng)
         self.eng.CreateHerdRaw(sc, d128, self.key)
-        self.gather = DPGather(self.eng, self.dist, self.rank, self.world, torch) if self.world > 1 else None
+        self.wire = wire
+        self.gather = DPGather(self.eng, self.dist, self.rank, self.world, torch, wire=wire) if self.world > 1 else None
         self.table_dps = {}                                            # rank 0: x -> (d, type)   (HashTable role)
         self.jumps = 0
         self.same_herd = 0
@@ -117,7 +118,14 @@ class Solver:
         if self.gather is not None:
             wo = self.wdiv2
             res = self.gather.step(len(items))
-            if self.rank == 0:
+            if self.rank == 0 and self.wire == "dp40":
+                # 40-byte records converted on the device (HashTable::Convert): table key = (h, 128 LSBs of x) exactly
+                # like the reference's hash table (HashTable.h:52-57), distance already un-biased and signed
+                for r, buf in res:
+                    for kidx, h, x128, dsigned, ktype in decode_dp40(buf):
+                        k = self._insert((h, x128), dsigned % ORDER, ktype)
+                        found = found or k
+            elif self.rank == 0:
                 for r, buf in res:
                     for x, dbias, kidx in decode_records(buf):
                         ktype = kidx % 2
@@ -159,12 +167,13 @@ def main(argv=None):
     ap.add_argument("--grid", default="")
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--max-steps", type=int, default=1 << 30)
+    ap.add_argument("--wire", default="item56", choices=["item56", "dp40"], help="DP record format gathered to rank 0")
     a = ap.parse_args(argv)
     start, end, pubs = ec.parse_config(a.config)
     grid = tuple(int(v) for v in a.grid.split(",")) if a.grid else None
     rc = 0
     for i, pub in enumerate(pubs):
-        s = Solver(start, end, pub, a.dp, grid, seed=a.seed)
+        s = Solver(start, end, pub, a.dp, grid, seed=a.seed, wire=a.wire)
         if s.rank == 0:
             print("Range width: 2^%d  kangaroos/GPU: %d  GPUs: %d  dp: %d" % (s.range_power, s.eng.nbKangaroo, s.world, a.dp), flush=True)
         key = s.run(a.max_steps)
