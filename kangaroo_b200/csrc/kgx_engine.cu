@@ -402,11 +402,9 @@ int kgx_convert_dps(kgx_engine* e, const uint64_t wild_offset[2], void** out) {
 void* kgx_dp_slab_device(kgx_engine* e) { return e->done >= 0 ? (void*)e->slab[e->done] : (void*)e->slab[e->cur]; }
 
 // ---- test / microbench hooks ----
-static char g_hook_err[256];
 #define CKH(call) do { cudaError_t _s = (call); if (_s != cudaSuccess) { snprintf(g_create_err, sizeof g_create_err, "%s: %s", #call, cudaGetErrorString(_s)); return -1; } } while (0)
 
 int kgx_test_field(int dev, int op, int n, const uint64_t* a, const uint64_t* b, uint64_t* out) {
-  (void)g_hook_err;
   CKH(cudaSetDevice(dev));
   u32 *da, *db, *dout;
   CKH(cudaMalloc(&da, (size_t)n * 32)); CKH(cudaMalloc(&db, (size_t)n * 32)); CKH(cudaMalloc(&dout, (size_t)n * 32));

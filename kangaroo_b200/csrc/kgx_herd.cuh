@@ -95,15 +95,18 @@ __global__ void herd_kernel(const u32* __restrict__ tab, const u32* __restrict__
   fe_mul(X, X, zi2);
   fe_mul(zi2, zi2, zi);
   fe_mul(Y, Y, zi2);
-  // canonical residues: one conditional subtraction of p (fe_mul leaves values < 2^256 congruent mod p)
-  {
-    u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pm[8] = {0xFFFFFC2Fu, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    bool gex = true, gey = true;     // X >= p ?
-    for (int w = 7; w >= 0; w--) { if (X[w] != pm[w]) { gex = X[w] > pm[w]; break; } }
-    for (int w = 7; w >= 0; w--) { if (Y[w] != pm[w]) { gey = Y[w] > pm[w]; break; } }
-    (void)z;
-    if (gex) { u32 c = 0x3D1u; u64 acc = (u64)X[0] + c; X[0] = (u32)acc; acc = (u64)X[1] + 1u + (acc >> 32); X[1] = (u32)acc; for (int w = 2; w < 8; w++) { acc = (u64)X[w] + (acc >> 32); X[w] = (u32)acc; } }
-    if (gey) { u32 c = 0x3D1u; u64 acc = (u64)Y[0] + c; Y[0] = (u32)acc; acc = (u64)Y[1] + 1u + (acc >> 32); Y[1] = (u32)acc; for (int w = 2; w < 8; w++) { acc = (u64)Y[w] + (acc >> 32); Y[w] = (u32)acc; } }
+  // canonical residues: fe_mul leaves values < 2^256 congruent mod p; subtract p once if needed
+  // (subtracting p mod 2^256 == adding 0x1000003D1)
+  const u32 pm[8] = {0xFFFFFC2Fu, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  for (int c = 0; c < 2; c++) {
+    u32* V = c ? Y : X;
+    bool ge = true;
+    for (int w = 7; w >= 0; w--) { if (V[w] != pm[w]) { ge = V[w] > pm[w]; break; } }
+    if (ge) {
+      u64 acc = (u64)V[0] + 0x3D1u; V[0] = (u32)acc;
+      acc = (u64)V[1] + 1u + (acc >> 32); V[1] = (u32)acc;
+      for (int w = 2; w < 8; w++) { acc = (u64)V[w] + (acc >> 32); V[w] = (u32)acc; }
+    }
   }
 #pragma unroll
   for (int w = 0; w < 8; w++) { px[i * 8 + w] = X[w]; py[i * 8 + w] = Y[w]; }

@@ -1,21 +1,23 @@
-// kgx_kernel.cuh -- the kangaroo jump kernel for sm_100a (B200).
+// kgx_kernel.cuh -- the kangaroo jump kernels for sm_100a (B200).
 //
-// Replaces the reference's GPU/GPUCompute.h:22-117 (ComputeKangaroos) + comp_kangaroos (GPUEngine.cu:35-40).
+// Replace the reference's GPU/GPUCompute.h:22-117 (ComputeKangaroos) + comp_kangaroos (GPUEngine.cu:35-40).
 // Same mathematics, different machine mapping:
 //
-//   reference : every thread owns 128 kangaroos in LOCAL memory (18.5 KB stack/thread), private Montgomery
-//               chain per thread, one _ModInv per thread per jump -> ~416 B/jump of local-memory traffic.
-//   here      : a CTA of 128 threads owns a TILE of 896 kangaroos whose whole state (x, y, d, running prefix
-//               product = 112 B each) stays in SHARED MEMORY for all NB_RUN=64 jumps of a launch; HBM sees each
-//               kangaroo once in and once out per launch (2.5 B/jump).  The Montgomery batch inverse spans
-//               the whole tile: per-thread chains (7 kangaroos) -> per-lane chains across the 4 warps ->
-//               XOR-butterfly product over the 32 lanes with warp shuffles -> ONE safegcd inverse per tile
-//               per jump (warp-uniform, no divergence) -> back down the same tree.
-//               Two CTAs are resident per SM so one tile's serial inverse overlaps the other's parallel phase.
+//   reference      : every thread owns 128 kangaroos in LOCAL memory (18.5 KB stack/thread): px/py/dx/subp arrays are
+//                    re-read and re-written through L1/L2 several times per jump (~416 B/jump), three passes.
+//   stream_kernel  : (default for herds >= 1e6) every thread owns a private group of G kangaroos that live in HBM as
+//                    coalesced 16-byte SoA chunks; ONE fused pass per jump reads prefix/x/y/d and writes x'/y'/d'/next
+//                    prefix (224 B/jump) with the next kangaroo prefetched into a second register buffer; no barriers,
+//                    no cross-thread traffic; per-thread variable-time safegcd inverse once per G jumps.
+//   jump_kernel    : (resident; default for small herds) a CTA of T threads owns a tile of T*K kangaroos whose whole
+//                    state stays in SHARED memory for all NB_RUN jumps of a launch (HBM 2.5 B/jump).  The batch inverse
+//                    spans the tile: per-thread chains -> per-lane chains across the warps -> XOR-butterfly product over
+//                    the 32 lanes with warp shuffles -> ONE warp-uniform inverse per tile per jump -> back down the tree;
+//                    several CTAs per SM overlap one tile's serial inverse with another's parallel phase.
 //
-//   The per-kangaroo pass fuses: back-substitution of this jump's inverse, the affine add, the distance
-//   update, the DP test, and the *next* jump's dx / prefix product (accumulated in the opposite order), so
-//   each jump is one sweep over shared memory: 5 ModMult + 1 ModSqr + 7 ModSub per kangaroo.
+//   Both use the same fused per-kangaroo pass: back-substitution of this jump's inverse, the affine add, the
+//   distance update, the DP test, and the *next* jump's dx / prefix product (accumulated in the order of this pass,
+//   consumed in reverse by the next): 5 ModMult + 1 ModSqr + 7 ModSub per jump.  DESIGN.md 3 has the measurements.
 #pragma once
 #include "kgx_field.cuh"
 #include "kgx_modinv.h"
