@@ -146,10 +146,10 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
   e->T = g_cfgs[e->cfg].T; e->K = g_cfgs[e->cfg].K; e->smemBytes = g_cfgs[e->cfg].smem; e->ctasPerSM = g_cfgs[e->cfg].ctas;
   {
     const char* mode = getenv("KGX_MODE");
-    // default: the streaming kernel for herds of a million kangaroos and more (it needs ~128 kangaroos per thread on
-    // every SM to amortise the per-thread inverse), the shared-memory tile kernel below that (its inverse is shared by a
-    // whole tile, so it keeps ~6.8 GJump/s down to ~300 k kangaroos) -- measured crossover, profiles/r1g_sweep.txt
-    e->streamMode = mode ? (strcmp(mode, "stream") == 0) : (KGX_DEFAULT_STREAM != 0 && e->n >= 1000000ull);
+    // default: the streaming kernel for herds of 400 k kangaroos and more (it wants many kangaroos per thread on every
+    // SM to amortise the per-thread inverse), the shared-memory tile kernel below that (its inverse is shared by a whole
+    // tile, so it keeps ~6.9 GJump/s down to ~270 k kangaroos) -- measured crossover, profiles/r1g_sweep.txt
+    e->streamMode = mode ? (strcmp(mode, "stream") == 0) : (KGX_DEFAULT_STREAM != 0 && e->n >= 400000ull);
     if (mode && strcmp(mode, "stream") && strcmp(mode, "resident")) {
       snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream or resident"); delete e; return nullptr;
     }
@@ -157,10 +157,11 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
       // kangaroos per thread: 128 (the reference's GPU_GRP_SIZE) when the herd fills two CTAs per SM with it; smaller
       // herds get a smaller group so that the grid still covers the chip (one wave of 2 CTAs/SM), at the price of more
       // inversions per jump.  KGX_STREAM_G overrides.
-      long long g = (long long)(e->n / ((u64)2 * prop.multiProcessorCount * 128));
+      const u64 slots = (u64)2 * prop.multiProcessorCount * 128;          // threads of one wave
+      long long g = (long long)((e->n + slots - 1) / slots);               // round UP: never more tiles than one wave
+      g = (g + 1) & ~1LL;
       if (g > 128) g = 128;
       if (g < 2) g = 2;
-      g &= ~1LL;
       if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
       if (g < 2 || g > 4096 || (g & 1)) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_G must be an even number in [2, 4096]"); delete e; return nullptr; }
       e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = 2;
