@@ -58,6 +58,11 @@ int kgx_set_params(kgx_engine* e, uint64_t dp_mask, const uint64_t* jd, const ui
 int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint64_t* d);   /* n x 4, n x 4, n x 2 */
 int kgx_download(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d);
 int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t py[4], const uint64_t d[2]);
+/* Asynchronous GetKangaroos for checkpoints (Kangaroo.cpp:618-626, Backup.cpp:449-572): _begin snapshots the
+ * herd in stream order (after the launch in flight) without blocking the caller or later launches; _read waits for that
+ * snapshot only and copies it to the host arrays (kIdx order, distances still biased). */
+int kgx_snapshot_begin(kgx_engine* e);
+int kgx_snapshot_read(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d);
 
 /* --- herd creation on the device (replaces the CPU side of Kangaroo::CreateHerd, Kangaroo.cpp:670-738):
  *     kangaroo i starts at scalars[i]*G, plus `key` when (i + first_type) is odd (wild).  scalars: n x 4 limbs (mod the

@@ -39,6 +39,8 @@ struct kgx_engine {
   int done = -1;               // slab of the most recently completed launch
   cudaStream_t stream = nullptr, copyStream = nullptr;
   cudaEvent_t evStart[2] = {nullptr, nullptr}, evStop[2] = {nullptr, nullptr};
+  cudaEvent_t evSnap = nullptr;   // snapshot (checkpoint) staging complete
+  bool snapPending = false;
   float lastMs = 0.f;
   unsigned long long* prof = nullptr;   // KGX_PROF=1: phase cycle counters
   u64 launches = 0;
@@ -107,6 +109,7 @@ void kgx_destroy(kgx_engine* e) {
   cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
   if (e->slabPinned) cudaFreeHost(e->slabPinned);
   for (int i = 0; i < 2; i++) { if (e->evStart[i]) cudaEventDestroy(e->evStart[i]); if (e->evStop[i]) cudaEventDestroy(e->evStop[i]); }
+  if (e->evSnap) cudaEventDestroy(e->evSnap);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copyStream) cudaStreamDestroy(e->copyStream);
   delete e;
@@ -247,6 +250,7 @@ static void free_staging(kgx_engine* e) {
 
 int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint64_t* d) {
   CK(e, cudaSetDevice(e->dev));
+  if (e->snapPending) { snprintf(e->err, sizeof e->err, "kgx_upload: snapshot pending (read it first)"); return -1; }
   if (ensure_staging(e)) return -1;
   CK(e, cudaMemcpyAsync(e->stgX, px, e->n * 32, cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaMemcpyAsync(e->stgY, py, e->n * 32, cudaMemcpyHostToDevice, e->stream));
@@ -262,6 +266,7 @@ int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint
 
 int kgx_download(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d) {
   CK(e, cudaSetDevice(e->dev));
+  if (e->snapPending) { snprintf(e->err, sizeof e->err, "kgx_download: snapshot pending (read it first)"); return -1; }
   if (ensure_staging(e)) return -1;
   u32 blocks = (u32)((e->n + 255) / 256);
   unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->T, e->K);   // stream order: after the in-flight launch
@@ -271,6 +276,37 @@ int kgx_download(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d) {
   CK(e, cudaMemcpyAsync(py, e->stgY, e->n * 32, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaMemcpyAsync(d, e->stgD, e->n * 16, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  free_staging(e);
+  return 0;
+}
+
+// ---- asynchronous checkpoint (reference: SolveKeyGPU parks on saveMutex while GetKangaroos copies the
+// whole herd with blocking memcpys, Kangaroo.cpp:618-626).  kgx_snapshot_begin() enqueues, in stream order (i.e. after the
+// launch in flight), a device-side copy of the herd into kIdx-ordered staging and returns at once; later launches run
+// on; kgx_snapshot_read() waits for that copy only and moves it to the host on the copy stream.
+int kgx_snapshot_begin(kgx_engine* e) {
+  CK(e, cudaSetDevice(e->dev));
+  if (e->snapPending) { snprintf(e->err, sizeof e->err, "kgx_snapshot_begin: previous snapshot not read"); return -1; }
+  if (ensure_staging(e)) return -1;
+  if (!e->evSnap) CK(e, cudaEventCreateWithFlags(&e->evSnap, cudaEventBlockingSync | cudaEventDisableTiming));
+  u32 blocks = (u32)((e->n + 255) / 256);
+  unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->T, e->K);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  CK(e, cudaEventRecord(e->evSnap, e->stream));
+  e->snapPending = true;
+  return 0;
+}
+
+int kgx_snapshot_read(kgx_engine* e, uint64_t* px, uint64_t* py, uint64_t* d) {
+  CK(e, cudaSetDevice(e->dev));
+  if (!e->snapPending) { snprintf(e->err, sizeof e->err, "kgx_snapshot_read: no snapshot pending"); return -1; }
+  CK(e, cudaStreamWaitEvent(e->copyStream, e->evSnap, 0));
+  CK(e, cudaMemcpyAsync(px, e->stgX, e->n * 32, cudaMemcpyDeviceToHost, e->copyStream));
+  CK(e, cudaMemcpyAsync(py, e->stgY, e->n * 32, cudaMemcpyDeviceToHost, e->copyStream));
+  CK(e, cudaMemcpyAsync(d, e->stgD, e->n * 16, cudaMemcpyDeviceToHost, e->copyStream));
+  CK(e, cudaStreamSynchronize(e->copyStream));
+  e->snapPending = false;
   free_staging(e);
   return 0;
 }

@@ -165,6 +165,17 @@ class GPUEngine:
         self._ck(self._lib.kgx_download(self._h, _p(ax), _p(ay), _p(ad)), "GetKangaroos")
         return ax, ay, ad
 
+    def SnapshotBegin(self):
+        """Asynchronous GetKangaroos (checkpoint path): snapshot after the launch in flight, do not block."""
+        self._ck(self._lib.kgx_snapshot_begin(self._h), "SnapshotBegin")
+
+    def SnapshotRead(self):
+        """-> (px, py, d) lists of ints (d unbiased, mod n) of the snapshot taken by SnapshotBegin."""
+        n = self.nbKangaroo
+        ax = np.empty((n, 4), dtype=np.uint64); ay = np.empty((n, 4), dtype=np.uint64); ad = np.empty((n, 2), dtype=np.uint64)
+        self._ck(self._lib.kgx_snapshot_read(self._h, _p(ax), _p(ay), _p(ad)), "SnapshotRead")
+        return _ints(ax), _ints(ay), [self._unbias(v, i) for i, v in enumerate(_ints(ad))]
+
     def SetKangaroosRaw(self, ax, ay, ad):
         n = self.nbKangaroo
         ax, ay, ad = _limbs(ax, 4), _limbs(ay, 4), _limbs(ad, 2)
