@@ -100,8 +100,8 @@ int      kgx_debug_prof(kgx_engine* e, uint64_t out[4]);
 /* --- device-side unit-test / microbenchmark hooks (kgx_field.cuh, kgx_modinv.h) --- */
 /* op: 0 = mul, 1 = sqr, 2 = sub, 3 = inv.  a, b, out: n x 4 limbs on the HOST. */
 int kgx_test_field(int dev, int op, int n, const uint64_t* a, const uint64_t* b, uint64_t* out);
-/* Batch-inverse microbench (BASELINE config 5): runs `launches` launches on a scratch herd with dp disabled,
- * returns total device ms. */
+/* Raw device throughput probes: kind 0 = IMAD.WIDE.U32 issue rate (the multiplier roofline bench.py reports against),
+ * 1 = ModMult chains, 2 = ModSqr chains, 3 = modular inverses.  *ms = device time, *ops = operations executed. */
 int kgx_bench_raw(int dev, int kind, int iters, float* ms, double* ops);
 
 #ifdef __cplusplus
