@@ -34,3 +34,21 @@ def test_parse_config_and_pubkeys(tmp_path):
 
 def test_dp_mask():
     assert dp_mask(0) == 0 and dp_mask(8) == 0xFF00000000000000 and dp_mask(64) == 0xFFFFFFFFFFFFFFFF and dp_mask(99) == 0xFFFFFFFFFFFFFFFF
+
+
+def test_random_herd_arrays_match_create_herd_rule():
+    """Kangaroo::CreateHerd distances (Kangaroo.cpp:696-704), vectorised: tame scalar = v, wild scalar = v - width/2 mod n,
+    stored distance = v (wild bias and shift cancel when wildOffset == width/2)."""
+    from kangaroo_b200.engine import random_herd_arrays, ORDER
+    for rp in (40, 64, 80, 109, 125):
+        w = ((1 << rp) - 1) >> 1
+        sc, d = random_herd_arrays(2000, rp, w, np.random.Generator(np.random.PCG64(rp)))
+        assert sc.shape == (2000, 4) and d.shape == (2000, 2)
+        vmax = 0
+        for i in range(2000):
+            v = int(d[i, 0]) | (int(d[i, 1]) << 64)
+            s = sum(int(sc[i, k]) << (64 * k) for k in range(4))
+            assert v < (1 << rp)
+            assert s == (v if i % 2 == 0 else (v - w) % ORDER)
+            vmax = max(vmax, v)
+        assert vmax >> (rp - 4)        # the top bits are populated: the range is actually covered
