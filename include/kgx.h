@@ -46,6 +46,16 @@ int  kgx_device_info(int dev, char* buf, int buflen);
 
 /* --- life cycle (GPUEngine ctor/dtor, GPUEngine.cu:144-263) --- */
 kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_found);
+/* Same, with the jump kernel chosen by the caller instead of by herd size: KGX_KERNEL_STREAM = per-thread groups
+ * streamed through HBM (the benchmarked kernel), KGX_KERNEL_RESIDENT = shared-memory tile kernel; stream_g = kangaroos
+ * per thread of the stream kernel (even, 2..4096; 0 = adaptive).  Used by the parity tests to pin BOTH kernels to the
+ * oracle and the reference fixtures on every grid. */
+#define KGX_KERNEL_AUTO     0
+#define KGX_KERNEL_STREAM   1
+#define KGX_KERNEL_RESIDENT 2
+kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t max_found, int kernel, int stream_g);
+/* 1 = stream kernel, 2 = resident kernel (what kgx_create / kgx_create_ex resolved to) */
+int         kgx_kernel_kind(kgx_engine* e);
 void        kgx_destroy(kgx_engine* e);
 const char* kgx_last_error(kgx_engine* e);      /* e may be NULL: error of the last failed kgx_create */
 uint64_t    kgx_num_kangaroos(kgx_engine* e);   /* groups * threads_per_group * 128 */

@@ -24,6 +24,8 @@ _SIGS = {
     "kgx_grid_default": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "kgx_device_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "kgx_create": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32]),
+    "kgx_create_ex": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),
+    "kgx_kernel_kind": (ctypes.c_int, [ctypes.c_void_p]),
     "kgx_destroy": (None, [ctypes.c_void_p]),
     "kgx_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "kgx_num_kangaroos": (ctypes.c_uint64, [ctypes.c_void_p]),

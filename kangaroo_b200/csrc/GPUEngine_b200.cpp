@@ -121,8 +121,16 @@ void GPUEngine::SetKangaroo(uint64_t kIdx, Int* px, Int* py, Int* d) {          
   if (kgx_patch(KGX(inputKangaroo), kIdx, x, y, dd) != 0) printf("GPUEngine: SetKangaroo: %s\n", kgx_last_error(KGX(inputKangaroo)));
 }
 
+// The reference prints a CUDA error on every failing call (GPUEngine.cu:549-553); its callers ignore the result and
+// keep looping (Kangaroo.cpp:572-575), so an engine that could not be created must at least say so -- once.
+static bool no_engine(const char* where) {
+  static bool said = false;
+  if (!said) { printf("GPUEngine: %s: engine not initialised (%s)\n", where, kgx_last_error(NULL)); said = true; }
+  return false;
+}
+
 bool GPUEngine::callKernel() {                                                  // GPUEngine.cu:540-557
-  if (!inputKangaroo) return false;
+  if (!inputKangaroo) return no_engine("Kernel");
   if (kgx_launch_async(KGX(inputKangaroo)) != 0) { printf("GPUEngine: Kernel: %s\n", kgx_last_error(KGX(inputKangaroo))); return false; }
   return true;
 }
@@ -135,7 +143,7 @@ bool GPUEngine::callKernelAndWait() {                                           
 
 bool GPUEngine::Launch(std::vector<ITEM>& hashFound, bool spinWait) {            // GPUEngine.cu:607-679
   hashFound.clear();
-  if (!inputKangaroo) return false;
+  if (!inputKangaroo) return no_engine("Launch");
   kgx_item* items = reinterpret_cast<kgx_item*>(outputItemPinned);
   uint32_t nItems = 0, nFound = 0;
   // waits for the launch in flight, starts the next one, then reads the finished slab back (double buffered)

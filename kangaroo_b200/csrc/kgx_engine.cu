@@ -116,6 +116,12 @@ void kgx_destroy(kgx_engine* e) {
 }
 
 kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_found) {
+  return kgx_create_ex(dev, groups, threads_per_group, max_found, KGX_KERNEL_AUTO, 0);
+}
+
+// kernel: KGX_KERNEL_AUTO / _STREAM / _RESIDENT; stream_g: kangaroos per thread of the stream kernel (0 = adaptive).
+// The environment (KGX_MODE, KGX_STREAM_G, KGX_CFG) only fills in what the arguments leave on "auto".
+kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t max_found, int kernel, int stream_g) {
   kgx_engine* e = new kgx_engine();
   auto fail = [&](const char* what, cudaError_t s) -> kgx_engine* {
     snprintf(g_create_err, sizeof g_create_err, "kgx_create: %s: %s", what, cudaGetErrorString(s));
@@ -149,6 +155,9 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
   e->T = g_cfgs[e->cfg].T; e->K = g_cfgs[e->cfg].K; e->smemBytes = g_cfgs[e->cfg].smem; e->ctasPerSM = g_cfgs[e->cfg].ctas;
   {
     const char* mode = getenv("KGX_MODE");
+    if (kernel == KGX_KERNEL_STREAM) mode = "stream";
+    else if (kernel == KGX_KERNEL_RESIDENT) mode = "resident";
+    else if (kernel != KGX_KERNEL_AUTO) { snprintf(g_create_err, sizeof g_create_err, "kgx_create_ex: bad kernel selector %d", kernel); delete e; return nullptr; }
     // default: the streaming kernel for herds of 400 k kangaroos and more (it wants many kangaroos per thread on every
     // SM to amortise the per-thread inverse), the shared-memory tile kernel below that (its inverse is shared by a whole
     // tile, so it keeps ~6.9 GJump/s down to ~270 k kangaroos) -- measured crossover, profiles/r1g_sweep.txt
@@ -165,8 +174,9 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
       g = (g + 1) & ~1LL;
       if (g > 128) g = 128;
       if (g < 2) g = 2;
-      if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
-      if (g < 2 || g > 4096 || (g & 1)) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_G must be an even number in [2, 4096]"); delete e; return nullptr; }
+      if (stream_g > 0) g = stream_g;
+      else if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
+      if (g < 2 || g > 4096 || (g & 1)) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: stream group size (KGX_STREAM_G) must be an even number in [2, 4096]"); delete e; return nullptr; }
       e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = 2;
     }
   }
@@ -202,6 +212,7 @@ kgx_engine* kgx_create(int dev, int groups, int threads_per_group, uint32_t max_
 }
 
 uint64_t kgx_num_kangaroos(kgx_engine* e) { return e->n; }
+int kgx_kernel_kind(kgx_engine* e) { return e->streamMode ? KGX_KERNEL_STREAM : KGX_KERNEL_RESIDENT; }
 uint64_t kgx_memory_bytes(kgx_engine* e) { return e->stateBytes + (e->pre ? e->nPadded * 32 : 0) + 2 * e->slabBytes + JT_WORDS * 4; }
 uint32_t kgx_max_found(kgx_engine* e) { return e->maxFound; }
 float kgx_last_launch_ms(kgx_engine* e) { return e->lastMs; }
@@ -328,6 +339,7 @@ int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t
 // feeds ComputePublicKeys); d128: n x 2 limbs (the biased distances to store); key: x[4], y[4].
 int kgx_create_herd(kgx_engine* e, const uint64_t* scalars, const uint64_t* d128, const uint64_t keyx[4], const uint64_t keyy[4], int first_type) {
   CK(e, cudaSetDevice(e->dev));
+  if (e->snapPending) { snprintf(e->err, sizeof e->err, "kgx_create_herd: snapshot pending (read it first)"); return -1; }
   if (!e->herdTab) {
     CK(e, cudaMalloc(&e->herdTab, 256 * 16 * 4));
     herd_table_kernel<<<1, 32, 0, e->stream>>>(e->herdTab);
@@ -336,25 +348,29 @@ int kgx_create_herd(kgx_engine* e, const uint64_t* scalars, const uint64_t* d128
   }
   if (ensure_staging(e)) return -1;
   u32 *dScal = nullptr, *dKey = nullptr;
-  CK(e, cudaMalloc(&dScal, e->n * 32));
-  CK(e, cudaMalloc(&dKey, 64));
   uint64_t key[8];
   memcpy(key, keyx, 32); memcpy(key + 4, keyy, 32);
-  CK(e, cudaMemcpyAsync(dScal, scalars, e->n * 32, cudaMemcpyHostToDevice, e->stream));
-  CK(e, cudaMemcpyAsync(dKey, key, 64, cudaMemcpyHostToDevice, e->stream));
-  CK(e, cudaMemcpyAsync(e->stgD, d128, e->n * 16, cudaMemcpyHostToDevice, e->stream));
-  herd_kernel<<<(u32)((e->n + 127) / 128), 128, 0, e->stream>>>(e->herdTab, dScal, dKey, first_type, e->n,
-                                                               reinterpret_cast<u32*>(e->stgX), reinterpret_cast<u32*>(e->stgY));
-  e->launches++;
-  CK(e, cudaGetLastError());
-  u32 blocks = (u32)((e->nPadded + 255) / 256);
-  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K);
-  e->launches++;
-  CK(e, cudaGetLastError());
-  CK(e, cudaStreamSynchronize(e->stream));
+  auto body = [&]() -> int {      // CK returns from the lambda, so the scratch buffers are always released below
+    CK(e, cudaMalloc(&dScal, e->n * 32));
+    CK(e, cudaMalloc(&dKey, 64));
+    CK(e, cudaMemcpyAsync(dScal, scalars, e->n * 32, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(dKey, key, 64, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->stgD, d128, e->n * 16, cudaMemcpyHostToDevice, e->stream));
+    herd_kernel<<<(u32)((e->n + 127) / 128), 128, 0, e->stream>>>(e->herdTab, dScal, dKey, first_type, e->n,
+                                                                 reinterpret_cast<u32*>(e->stgX), reinterpret_cast<u32*>(e->stgY));
+    e->launches++;
+    CK(e, cudaGetLastError());
+    u32 blocks = (u32)((e->nPadded + 255) / 256);
+    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K);
+    e->launches++;
+    CK(e, cudaGetLastError());
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+  };
+  const int rc = body();
   cudaFree(dScal); cudaFree(dKey);
   free_staging(e);
-  return 0;
+  return rc;
 }
 
 int kgx_launch_async(kgx_engine* e) {
@@ -385,7 +401,9 @@ int kgx_collect(kgx_engine* e, kgx_item* items, uint32_t cap, uint32_t* n_items,
   int sidx = e->cur;
   if (e->inflight) {
     if (spin) {
-      while (cudaEventQuery(e->evStop[sidx]) == cudaErrorNotReady) { }
+      cudaError_t q;
+      while ((q = cudaEventQuery(e->evStop[sidx])) == cudaErrorNotReady) { }
+      CK(e, q);                                       // anything but success / not-ready is a failed launch
     } else {
       CK(e, cudaEventSynchronize(e->evStop[sidx]));   // blocking-sync event: the host thread sleeps (GPUEngine.cu:620-629)
     }

@@ -19,6 +19,13 @@ __device__ __forceinline__ void fe_dbl(u32* r, const u32* a) {   // 2a mod p
   fe_sub(r, a, n);
 }
 
+// a == 0 (mod p)?  fe_mul / fe_sub results live in [0, 2^256): the only representatives of 0 are 0 and p.
+__device__ __forceinline__ bool fe_is_zero_modp(const u32* a) {
+  const u32 orv = a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+  const u32 andv = a[2] & a[3] & a[4] & a[5] & a[6] & a[7];
+  return orv == 0u || (andv == 0xFFFFFFFFu && a[1] == 0xFFFFFFFEu && a[0] == 0xFFFFFC2Fu);
+}
+
 // tab[i] = 2^i * G (affine, 16 words each: x then y), i = 0..255.  One thread; 255 affine doublings.
 __global__ void herd_table_kernel(u32* tab) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -76,6 +83,24 @@ __global__ void herd_kernel(const u32* __restrict__ tab, const u32* __restrict__
     fe_mul(s2, qy, zz); fe_mul(s2, s2, Z);
     fe_sub(h, u2, X);
     fe_sub(r, s2, Y);
+    if (fe_is_zero_modp(h)) {
+      // same x: the term equals the accumulator (double it) or its negative (sum = point at infinity).  Cannot happen
+      // between table terms for a scalar < n; happens for the key term when d*G == +-key (a wild kangaroo created on
+      // the key itself).  The reference's AddDirect (SECP256K1.cpp:238-262) would divide by zero -> garbage; here the
+      // group law is followed.
+      if (!fe_is_zero_modp(r)) { inf = true; continue; }
+      // Jacobian doubling, a = 0: S = 4 X Y^2 ; M = 3 X^2 ; X' = M^2 - 2S ; Y' = M (S - X') - 8 Y^4 ; Z' = 2 Y Z
+      u32 yy[8], S[8], M[8], m2[8], y4[8], nx[8], ny[8], nz[8];
+      fe_sqr(yy, Y);
+      fe_mul(S, X, yy); fe_dbl(S, S); fe_dbl(S, S);
+      fe_sqr(m2, X); fe_dbl(M, m2); { u32 ng[8]; fe_neg(ng, m2); fe_sub(M, M, ng); }
+      fe_sqr(nx, M); fe_sub(nx, nx, S); fe_sub(nx, nx, S);
+      fe_sqr(y4, yy); fe_dbl(y4, y4); fe_dbl(y4, y4); fe_dbl(y4, y4);
+      fe_sub(ny, S, nx); fe_mul(ny, ny, M); fe_sub(ny, ny, y4);
+      fe_mul(nz, Y, Z); fe_dbl(nz, nz);
+      fe_copy(X, nx); fe_copy(Y, ny); fe_copy(Z, nz);
+      continue;
+    }
     fe_sqr(hh, h);
     fe_mul(hhh, hh, h);
     fe_mul(v, X, hh);
@@ -88,6 +113,14 @@ __global__ void herd_kernel(const u32* __restrict__ tab, const u32* __restrict__
     fe_sub(Y, v, hhh);                           // Y3
     fe_mul(Z, Z, h);                             // Z3
     fe_copy(X, t);
+  }
+  if (inf) {
+    // scalar 0 (tame) or d*G == -key (wild): the point at infinity has no affine form; store (0, 0) -- not on the curve,
+    // the walk from it is meaningless but harmless (probability ~2^-rangePower; the reference stores an equally
+    // meaningless Z = 0 projective conversion, SECP256K1.cpp:59-87).
+#pragma unroll
+    for (int w = 0; w < 8; w++) { px[i * 8 + w] = 0; py[i * 8 + w] = 0; }
+    return;
   }
   u32 zi[8], zi2[8];
   modinv256(zi, Z);

@@ -5,7 +5,7 @@
 //
 //   reference      : every thread owns 128 kangaroos in LOCAL memory (18.5 KB stack/thread): px/py/dx/subp arrays are
 //                    re-read and re-written through L1/L2 several times per jump (~416 B/jump), three passes.
-//   stream_kernel  : (default for herds >= 1e6) every thread owns a private group of G kangaroos that live in HBM as
+//   stream_kernel  : (default for herds >= 4e5 kangaroos, kgx_engine.cu) every thread owns a private group of G kangaroos that live in HBM as
 //                    coalesced 16-byte SoA chunks; ONE fused pass per jump reads prefix/x/y/d and writes x'/y'/d'/next
 //                    prefix (224 B/jump) with the next kangaroo prefetched into a second register buffer; no barriers,
 //                    no cross-thread traffic; per-thread variable-time safegcd inverse once per G jumps.

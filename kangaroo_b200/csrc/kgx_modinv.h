@@ -1,11 +1,16 @@
 // kgx_modinv.h -- modular inverse mod p = 2^256 - 0x1000003D1, variable time, host+device.
 //
 // Replaces the reference's GPU/GPUMath.h:700-803 (_ModInv: DRS62 "delayed right shift" divsteps on 64-bit
-// limbs, which sm_100a has to emulate).  This is an independent implementation of the Bernstein-Yang
-// "safegcd" divstep iteration sized for a 32-bit integer datapath: batches of 30 divsteps on the low words,
-// 2x2 transition matrices with 32-bit signed entries applied to (f,g) and (d,e) held as 9 signed 30-bit
-// limbs, so every product is one native 32x32->64 IMAD.WIDE.  Result contract = the reference's: the
-// canonical inverse in [0,p), and inv(0) = 0 (GPUMath.h:785-801, IntMod.cpp:560-569).
+// limbs, which sm_100a has to emulate).  Algorithm and structure: the Bernstein-Yang "safegcd" divstep iteration in
+// the variable-time signed-30-bit-limb form published by libsecp256k1 (src/modinv32_impl.h, MIT licence, P. Wuille):
+// divsteps_30_var / update_de_30 / update_fg_30 / normalize_30 and the f*g*(f^2-2) 6-bit inverse trick follow that
+// design -- third-party public code, NOT the reference -- re-typed here for one fixed modulus p (constants folded,
+// host+device, static register indexing).  Batches of 30 divsteps on the low words, 2x2 transition matrices with
+// 32-bit signed entries applied to (f,g) and (d,e) held as 9 signed 30-bit limbs, so every product is one native
+// 32x32->64 IMAD.WIDE.  Result contract = the reference's: the canonical inverse in [0,p), and inv(0) = 0
+// (GPUMath.h:785-801, IntMod.cpp:560-569).  Inputs are expected in [0, 2^256); the jump path only feeds products of
+// fe_mul, i.e. values < 2^256 congruent to their residue.  (Input exactly p is not reduced first: the host twin
+// returns 1 for it, not 0 -- unreachable from the jump path, probability 2^-256.)
 //
 // In the jump kernel every lane of the inverting warp runs this on the SAME value (the tile product after
 // the butterfly), so all data-dependent control flow is warp-uniform: no divergence.
@@ -170,7 +175,7 @@ KGX_HD void modinv256(uint32_t out[8], const uint32_t in[8]) {
     int32_t cond = g.v[0] | g.v[1] | g.v[2] | g.v[3] | g.v[4] | g.v[5] | g.v[6] | g.v[7] | g.v[8];
     if (cond == 0) break;
   }
-  // gcd is |f| = 1 for invertible input; for 0 (or a multiple of p) f = +-p and d = 0.
+  // gcd is |f| = 1 for invertible input; for 0 f = +-p and d = 0.
   normalize_30(&d, f.v[8]);
   out[0] = (uint32_t)d.v[0] | ((uint32_t)d.v[1] << 30);
   out[1] = ((uint32_t)d.v[1] >> 2) | ((uint32_t)d.v[2] << 28);

@@ -58,7 +58,11 @@ def _p(a):
 
 
 class GPUEngine:
-    def __init__(self, nbThreadGroup, nbThreadPerGroup, gpuId=0, maxFound=65536):
+    KERNELS = {"auto": 0, "stream": 1, "resident": 2}
+
+    def __init__(self, nbThreadGroup, nbThreadPerGroup, gpuId=0, maxFound=65536, kernel="auto", stream_g=0):
+        """kernel / stream_g are not in the reference constructor (GPUEngine.cu:144): they pin the jump kernel
+        (kgx_create_ex) so that the parity tests can run every case on both; "auto" is the product default."""
         self._lib = load_library()
         self._h = None
         self.initialised = False
@@ -67,7 +71,7 @@ class GPUEngine:
         self.nbThread = nbThreadGroup * nbThreadPerGroup
         self.maxFound = maxFound
         self.lostWarning = False
-        h = self._lib.kgx_create(gpuId, nbThreadGroup, nbThreadPerGroup, maxFound)
+        h = self._lib.kgx_create_ex(gpuId, nbThreadGroup, nbThreadPerGroup, maxFound, self.KERNELS[kernel], int(stream_g))
         if not h:
             # the reference prints and leaves initialised=false (GPUEngine.cu:152-170); a Python mirror raising is the
             # loud equivalent -- there is no CPU path to fall back to.
@@ -78,6 +82,7 @@ class GPUEngine:
         name, sms, _, _, _ = buf.value.decode().split("|")
         self.deviceName = "GPU #%d %s (%sx%d cores) Grid(%dx%d)" % (gpuId, name, sms, 128, nbThreadGroup, nbThreadPerGroup)
         self._items = (Item * maxFound)()
+        self.kernel = {1: "stream", 2: "resident"}[self._lib.kgx_kernel_kind(self._h)]
         self.initialised = True
 
     # -- bookkeeping -------------------------------------------------------------------------------------

@@ -25,3 +25,14 @@ def reference():
     if not kgo.reference_available():
         pytest.skip("reference build (oracle/_ref/libkref.so) not available")
     return kgo.Reference()
+
+
+# Every oracle / reference-fixture parity test runs on BOTH jump kernels (kgx_create_ex): "stream128" is the benchmarked
+# configuration (stream kernel, 128 kangaroos per thread, what the default 296x128 grid resolves to), "stream" the
+# adaptive group size small grids get, "resident" the shared-memory tile kernel.
+KERNEL_VARIANTS = {"stream128": dict(kernel="stream", stream_g=128), "stream": dict(kernel="stream"), "resident": dict(kernel="resident")}
+
+
+@pytest.fixture(params=sorted(KERNEL_VARIANTS))
+def kernel(request):
+    return KERNEL_VARIANTS[request.param]

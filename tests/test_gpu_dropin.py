@@ -14,10 +14,12 @@ BIN = os.path.join(ROOT, "build", "kangaroo_b200")
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def run(args, timeout=600):
+def run(args, timeout=600, env=None):
     if not os.path.exists(BIN):
         pytest.skip("build/kangaroo_b200 not built (needs the reference sources at build time)")
-    p = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
     return p.stdout + p.stderr
 
 
@@ -25,6 +27,17 @@ def test_reference_check_gpu_vs_cpu():
     out = run(["-gpu", "-check", "-g", "8,128"])       # 131072 kangaroos -> ~32k DPs at dp=8 (< 65536 buffer)
     assert "CPU/GPU ok" in out, out[-3000:]
     assert "DP Mismatch" not in out and "not ok" not in out
+
+
+@pytest.mark.parametrize("env", [{"KGX_MODE": "stream", "KGX_STREAM_G": "128"}, {"KGX_MODE": "stream"}, {"KGX_MODE": "resident"}],
+                         ids=["stream128", "stream-adaptive", "resident"])
+def test_reference_check_largest_grid_on_each_kernel(env):
+    """Check.cpp hard-codes dp = 8 and a 65536-record DP buffer (:417, :492), so the largest herd its DP comparison can
+    hold is ~2.6e5 kangaroos (expected DPs = nb * 64 / 256 < 65536): `-g 15,128` = 245,760 kangaroos -> ~61.4 k DPs.
+    Run on the benchmarked stream kernel (G = 128, as on the default grid), the adaptive group size, and the tile kernel."""
+    out = run(["-gpu", "-check", "-g", "15,128"], timeout=1200, env=env)
+    assert "CPU/GPU ok" in out, out[-3000:]
+    assert "DP Mismatch" not in out and "not ok" not in out and "items lost" not in out
 
 
 def test_reference_check_odd_grid():
