@@ -65,7 +65,7 @@ def build_library(verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd, cwd=CSRC)
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", HOSTTEST_PATH, os.path.join(CSRC, "kgx_hosttest.cpp")])
+    subprocess.check_call(["g++", "-O2", "-frounding-math", "-ffp-contract=off", "-fPIC", "-shared", "-o", HOSTTEST_PATH, os.path.join(CSRC, "kgx_hosttest.cpp")])
     return LIB_PATH
 
 

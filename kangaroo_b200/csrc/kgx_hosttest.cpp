@@ -27,3 +27,20 @@ extern "C" int kgx_host_modinv_batches(const uint64_t in[4]) {
   }
   return n;
 }
+
+// FP64-pipe multiplier (kgx_field_fp64.cuh): 512-bit product / square through the 52-bit-limb DFMA scheme, on the host
+// with the FPU in round-toward-zero (the device uses fma.rz).  out: 8 x u64 limbs.
+#include <cfenv>
+#include "kgx_field_fp64.cuh"
+extern "C" void kgx_host_mul512_fp64(uint64_t out[8], const uint64_t a[4], const uint64_t b[4], int square) {
+  uint32_t a32[8], b32[8], w[16];
+  for (int i = 0; i < 4; i++) { a32[2 * i] = (uint32_t)a[i]; a32[2 * i + 1] = (uint32_t)(a[i] >> 32); b32[2 * i] = (uint32_t)b[i]; b32[2 * i + 1] = (uint32_t)(b[i] >> 32); }
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+  double da[5], db[5];
+  kgx::fe_to_d52(da, a32);
+  kgx::fe_to_d52(db, b32);
+  if (square) kgx::kgx_sqr512_d52(w, da); else kgx::kgx_mul512_d52(w, da, db);
+  fesetround(old);
+  for (int i = 0; i < 8; i++) out[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+}

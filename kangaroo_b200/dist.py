@@ -84,6 +84,37 @@ class DPGather:
         return out
 
 
+def _step_flat(self, n_found):
+    """Like step(), but rank 0 receives every rank's records in ONE contiguous device tensor (rank r at offset r*cap*rec),
+    so that the whole step's DPs reach the host with a single copy.  Returns (counts list, cap, tensor) on rank 0, None elsewhere."""
+    torch, dist = self.torch, self.dist
+    cnt = min(int(n_found), self.max_found)
+    mine = torch.tensor([cnt], dtype=torch.int32, device=self.device)
+    counts = torch.empty(self.world, dtype=torch.int32, device=self.device)
+    dist.all_gather_into_tensor(counts, mine)
+    counts_h = counts.cpu().tolist()
+    cap = max(ROUND, (max(counts_h) + ROUND - 1) // ROUND * ROUND)
+    cap = min(cap, self.max_found)
+    local = self._slab_fn()[4:4 + cap * self.rec]
+    out = None
+    if self.rank == 0:
+        if getattr(self, "_flat", None) is None:
+            self._flat = torch.empty(self.world * self.max_found * self.rec, dtype=torch.uint8, device=self.device)
+        n = cap * self.rec
+        bufs = [self._flat[r * n:(r + 1) * n] for r in range(self.world)]
+        dist.gather(local, bufs, dst=0)
+        out = (counts_h, cap, self._flat)
+    else:
+        dist.gather(local, None, dst=0)
+    if self.device.type == "cuda":
+        torch.cuda.current_stream().synchronize()   # the slab is recycled by the launch after next
+    self.total_gathered += sum(counts_h)
+    return out
+
+
+DPGather.step_flat = _step_flat
+
+
 def decode_records(buf):
     """uint8 tensor/bytes of 56-byte records -> list of (x, d_biased, kidx) Python ints (GPUEngine.cu:653-671)."""
     b = bytes(buf.cpu().numpy().tobytes()) if hasattr(buf, "cpu") else bytes(buf)

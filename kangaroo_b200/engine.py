@@ -239,6 +239,15 @@ class GPUEngine:
         xs = _ints(raw[:, 0:4]); ds = _ints(raw[:, 4:6]); ks = raw[:, 6].tolist()
         return [ITEM(x, self._unbias(d, kk), int(kk)) for x, d, kk in zip(xs, ds, ks)]
 
+    def collect_count(self, spinWait=False, relaunch=True):
+        """Launch() without the host copy of the records: wait for the launch in flight, (re)launch, return how many DPs it
+        produced.  The records stay in the device slab (dp_slab_device_ptr / convert_dps_device_ptr) for the NCCL gather."""
+        n_items, n_found = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._ck(self._lib.kgx_collect(self._h, self._items, 0, ctypes.byref(n_items), ctypes.byref(n_found),
+                                       int(bool(spinWait)), int(bool(relaunch))), "Launch")
+        self.lastFound = n_found.value
+        return int(n_found.value)
+
     def callKernelAndWait(self):
         ok = self.callKernel()
         self._ck(self._lib.kgx_sync(self._h), "callKernelAndWait")

@@ -4,10 +4,21 @@ per GPU and an NCCL gather of the DP records to rank 0 (kangaroo_b200/dist.py). 
 exercise the engine end to end (BASELINE config 4) -- the full-featured caller remains the reference's own program
 linked against the engine.
 
+Per step (= one GPUEngine::Launch on every rank) nothing on the data path is Python:
+  engine      kgx_collect(cap=0, relaunch=1): wait for launch i, start launch i+1, no host copy of records
+  device      kgx_convert_dps: HashTable::Convert of launch i's DPs -> 40-byte `DP` records (Kangaroo.h:94-101)
+  NCCL        all_gather(count) + gather(records) to rank 0          (dist.DPGather, wire "dp40")
+  rank 0      one D2H copy -> kgi_add: the reference's HashTable, bucket-sharded multi-threaded insert (ingest.DPTable)
+              -> events: KGI_EV_COLLISION -> kgi_resolve (CollisionCheck/CheckKey with the reference's Secp256K1)
+                         KGI_EV_RESET     -> (rank, kIdx) sent back to the owner, which re-creates that kangaroo
+                                             (Kangaroo.cpp:601-609: CreateHerd(1) + SetKangaroo)
+  all ranks   one small broadcast: [stop, n_resets, (rank, kIdx) ...]
+
   single GPU :  python -m kangaroo_b200.solver in.txt --dp 12
   N GPUs     :  torchrun --nproc-per-node N -m kangaroo_b200.solver in.txt --dp 12
 """
 import argparse
+import ctypes
 import os
 import sys
 import time
@@ -16,9 +27,11 @@ import numpy as np
 
 from . import ecmath as ec
 from .engine import GPUEngine, NB_JUMP, NB_RUN, WILD, random_herd_arrays
-from .dist import DPGather, decode_records, decode_dp40
+from .dist import DPGather, SlabView, DP40_BYTES
+from .ingest import DPTable, EV_RESET, EV_COLLISION
 
 ORDER = ec.N
+MAX_RESETS = 255          # per step, carried in the control broadcast
 
 
 def create_jump_table(range_power):
@@ -49,7 +62,7 @@ def dp_mask(bits):
 
 
 class Solver:
-    def __init__(self, start, end, pub, dp_bits, grid=None, max_found=1 << 17, seed=None, wire="item56"):
+    def __init__(self, start, end, pub, dp_bits, grid=None, max_found=1 << 17, seed=None, ingest_threads=0):
         import torch
         self.torch = torch
         self.rank = int(os.environ.get("RANK", "0"))
@@ -62,7 +75,7 @@ class Solver:
             if not dist.is_initialized():
                 dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
-        self.start, self.end, self.pub = start, end, pub
+        self.start, self.end, self.pub, self.dp_bits = start, end, pub, dp_bits
         width = end - start
         self.range_power = width.bit_length()                         # Kangaroo::InitRange (:877-890)
         self.wdiv2 = width >> 1
@@ -75,89 +88,118 @@ class Solver:
         self.eng.SetWildOffset(self.wdiv2)
         # Kangaroo::CreateHerd (:670-738): tame d in [0, 2^rangePower), wild d - width/2; points on the device
         n = self.eng.nbKangaroo
-        rng = np.random.Generator(np.random.PCG64((seed if seed is not None else int(time.time())) * 1000 + self.rank))
-        sc, d128 = random_herd_arrays(n, self.range_power, self.wdiv2, rng)
+        self.rng = np.random.Generator(np.random.PCG64((seed if seed is not None else int(time.time())) * 1000 + self.rank))
+        sc, d128 = random_herd_arrays(n, self.range_power, self.wdiv2, self.rng)
         self.eng.CreateHerdRaw(sc, d128, self.key)
-        self.wire = wire
-        self.gather = DPGather(self.eng, self.dist, self.rank, self.world, torch, wire=wire) if self.world > 1 else None
-        self.table_dps = {}                                            # rank 0: x -> (d, type)   (HashTable role)
+        self.gather = DPGather(self.eng, self.dist, self.rank, self.world, torch, wire="dp40") if self.world > 1 else None
+        self.dps = DPTable(threads=ingest_threads) if self.rank == 0 else None      # rank 0: the reference HashTable
+        self._host = torch.empty(self.world * max_found * DP40_BYTES, dtype=torch.uint8).pin_memory() if self.rank == 0 else None
+        self._ctrl = torch.zeros(2 + 2 * MAX_RESETS, dtype=torch.int64, device="cuda")
         self.jumps = 0
         self.same_herd = 0
+        self.resets_done = 0
+        self.t_ingest = 0.0
+        self.stop = False
 
-    # rank 0 only -----------------------------------------------------------------------------------------------
-    def _check_key(self, td, wd):
-        """Kangaroo::CheckKey (Kangaroo.cpp:218-253): the four sign combinations, against key and -key."""
-        for t in range(4):
-            d1 = (-td) % ORDER if t & 1 else td
-            d2 = (-wd) % ORDER if t & 2 else wd
-            pk = (d1 + d2) % ORDER
-            pt = ec.mul(pk)
-            if pt == self.key:
-                return (pk + self.start) % ORDER
-            if pt == ec.neg(self.key):
-                return (-pk + self.start) % ORDER
-        return None
+    # -- rank 0: ingest -------------------------------------------------------------------------------------------
+    def _ingest(self, segments):
+        """segments: list of (rank, uint8 numpy view of that rank's 40-byte records).  Returns (key or None, resets)."""
+        found, resets = None, []
+        t0 = time.perf_counter()
+        for r, buf in segments:
+            if buf.size == 0:
+                continue
+            for kind, rk, kidx, d_old, d_new in self.dps.add_dp40(buf, r):
+                if kind == EV_COLLISION and found is None:
+                    found = self.dps.resolve(d_old, d_new, self.key, self.start)     # Kangaroo.cpp:255-302
+                    if found is None:
+                        resets.append((rk, kidx))                                    # "unexpected wrong collision, reset kangaroo"
+                elif kind == EV_RESET:
+                    resets.append((rk, kidx))
+        self.t_ingest += time.perf_counter() - t0
+        return found, resets
 
-    def _insert(self, x, d, ktype):
-        """HashTable::Add + Kangaroo::CollisionCheck (Kangaroo.cpp:255-330) on a dict keyed by x."""
-        old = self.table_dps.get(x)
-        if old is None:
-            self.table_dps[x] = (d, ktype)
-            return None
-        if old[1] == ktype:
-            self.same_herd += (old[0] != d)
-            return None
-        td, wd = (old[0], d) if ktype == WILD else (d, old[0])
-        return self._check_key(td, wd)
+    def _reset_kangaroo(self, kidx):
+        """Kangaroo.cpp:601-609: CreateHerd(1, type) + SetKangaroo(kIdx) on the owning engine."""
+        v = int(self.rng.integers(0, 1 << 62)) | (int(self.rng.integers(0, 1 << 62)) << 62) | (int(self.rng.integers(0, 1 << 62)) << 124)
+        v &= (1 << self.range_power) - 1
+        if kidx % 2 == WILD:
+            d = (v - self.wdiv2) % ORDER
+            pos = ec.add(self.key, ec.mul(d))
+        else:
+            d = v
+            pos = ec.mul(d)
+        if pos is None:
+            return
+        self.eng.SetKangaroo(kidx, pos[0], pos[1], d)
+        self.resets_done += 1
 
     def step(self):
         """one Launch on every rank; returns the private key on rank 0 when found (None otherwise)"""
-        items = self.eng.Launch()
+        torch = self.torch
+        n_found = self.eng.collect_count(relaunch=True)                  # launch i done, launch i+1 running
+        cnt = min(n_found, self.eng.maxFound)
         self.jumps += self.eng.nbKangaroo * NB_RUN * self.world
-        found = None
+        found, resets = None, []
         if self.gather is not None:
-            wo = self.wdiv2
-            res = self.gather.step(len(items))
-            if self.rank == 0 and self.wire == "dp40":
-                # 40-byte records converted on the device (HashTable::Convert): table key = (h, 128 LSBs of x) exactly
-                # like the reference's hash table (HashTable.h:52-57), distance already un-biased and signed
-                for r, buf in res:
-                    for kidx, h, x128, dsigned, ktype in decode_dp40(buf):
-                        k = self._insert((h, x128), dsigned % ORDER, ktype)
-                        found = found or k
-            elif self.rank == 0:
-                for r, buf in res:
-                    for x, dbias, kidx in decode_records(buf):
-                        ktype = kidx % 2
-                        d = (dbias - wo) % ORDER if ktype == WILD else dbias       # GPUEngine.cu:672
-                        k = self._insert(x, d, ktype)
-                        found = found or k
-        elif self.rank == 0:
-            for it in items:
-                k = self._insert(it.x, it.d, it.kIdx % 2)
-                found = found or k
+            res = self.gather.step_flat(cnt)                                # rank 0: (counts, cap, device tensor [world*cap*40])
+            if self.rank == 0:
+                counts, cap, flat = res
+                nbytes = self.world * cap * DP40_BYTES
+                self._host[:nbytes].copy_(flat[:nbytes], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                h = self._host.numpy()
+                segs = [(r, h[r * cap * DP40_BYTES: r * cap * DP40_BYTES + counts[r] * DP40_BYTES]) for r in range(self.world)]
+                found, resets = self._ingest(segs)
+        else:
+            if cnt:
+                ptr = self.eng.convert_dps_device_ptr()
+                dev = torch.as_tensor(SlabView(ptr + 4, cnt * DP40_BYTES), device="cuda")
+                self._host[:cnt * DP40_BYTES].copy_(dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                found, resets = self._ingest([(0, self._host.numpy()[:cnt * DP40_BYTES])])
+        # control word: stop flag + kangaroos to re-create, back to their owners
         if self.dist is not None:
-            flag = self.torch.tensor([1 if found else 0], dtype=self.torch.int32, device="cuda")
-            self.dist.broadcast(flag, 0)
-            self.stop = bool(flag.item())
+            if self.rank == 0:
+                resets = resets[:MAX_RESETS]
+                c = [1 if found is not None else 0, len(resets)] + [v for rk in resets for v in rk]
+                self._ctrl[:len(c)].copy_(torch.tensor(c, dtype=torch.int64))
+            self.dist.broadcast(self._ctrl, 0)
+            c = self._ctrl.cpu().tolist()
+            self.stop = bool(c[0])
+            resets = [(c[2 + 2 * i], c[3 + 2 * i]) for i in range(c[1])]
         else:
             self.stop = found is not None
+        for rk, kidx in resets:
+            self.same_herd += 1
+            if rk == self.rank and not self.stop:
+                self._reset_kangaroo(kidx)
         return found
 
     def run(self, max_steps=1 << 30, verbose=True):
         self.eng.callKernel()
         t0 = time.time()
         key = None
+        steps = 0
         for s in range(max_steps):
             key = self.step()
-            if verbose and self.rank == 0 and (s % 16 == 15 or self.stop):
+            steps += 1
+            if verbose and self.rank == 0 and (s % 64 == 63 or self.stop):
                 dt = time.time() - t0
-                print("[%6.1fs] 2^%.2f jumps  %.0f MJump/s  %d DPs  same-herd %d" %
-                      (dt, np.log2(max(self.jumps, 1)), self.jumps / dt / 1e6, len(self.table_dps), self.same_herd), flush=True)
+                print("[%6.1fs] 2^%.2f jumps  %.0f MJump/s  %d DPs  dead %d  ingest %.1f ms/step" %
+                      (dt, np.log2(max(self.jumps, 1)), self.jumps / dt / 1e6, len(self.dps), self.same_herd,
+                       1e3 * self.t_ingest / steps), flush=True)
             if self.stop:
                 break
         self.eng.sync()
+        self.elapsed = time.time() - t0
+        self.steps = steps
         return key
+
+    def close(self):
+        self.eng.close()
+        if self.dps is not None:
+            self.dps.close()
 
 
 def main(argv=None):
@@ -167,22 +209,29 @@ def main(argv=None):
     ap.add_argument("--grid", default="")
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--max-steps", type=int, default=1 << 30)
-    ap.add_argument("--wire", default="item56", choices=["item56", "dp40"], help="DP record format gathered to rank 0")
+    ap.add_argument("--ingest-threads", type=int, default=0, help="workers of the rank-0 DP table (0 = min(8, cores))")
+    ap.add_argument("--save-work", default="", help="write the rank-0 DP table as a reference work file (HEADW) at the end")
     a = ap.parse_args(argv)
     start, end, pubs = ec.parse_config(a.config)
     grid = tuple(int(v) for v in a.grid.split(",")) if a.grid else None
     rc = 0
     for i, pub in enumerate(pubs):
-        s = Solver(start, end, pub, a.dp, grid, seed=a.seed, wire=a.wire)
+        s = Solver(start, end, pub, a.dp, grid, seed=a.seed, ingest_threads=a.ingest_threads)
         if s.rank == 0:
-            print("Range width: 2^%d  kangaroos/GPU: %d  GPUs: %d  dp: %d" % (s.range_power, s.eng.nbKangaroo, s.world, a.dp), flush=True)
+            print("Range width: 2^%d  kangaroos/GPU: %d  GPUs: %d  dp: %d  ingest threads: %d" %
+                  (s.range_power, s.eng.nbKangaroo, s.world, a.dp, s.dps.threads), flush=True)
         key = s.run(a.max_steps)
         if s.rank == 0:
+            print("Solver rate: %.0f MJump/s over %d steps (%.2f s); rank-0 ingest %.2f ms/step; %d DPs; %d dead kangaroos re-created" %
+                  (s.jumps / s.elapsed / 1e6, s.steps, s.elapsed, 1e3 * s.t_ingest / max(s.steps, 1), len(s.dps), s.same_herd))
+            if a.save_work:
+                s.dps.save_work(a.save_work, a.dp, start, end, pub, total_count=s.jumps, total_time=s.elapsed)
+                print("work file written: %s" % a.save_work)
             if key is not None and ec.mul(key) == pub:
                 print("Key#%2d Pub:  0x%064X\n       Priv: 0x%X" % (i, pub[0], key))
             else:
                 print("Key#%2d not found" % i); rc = 1
-        s.eng.close()
+        s.close()
     try:
         import torch.distributed as dist
         if dist.is_initialized():

@@ -55,3 +55,29 @@ def test_host_modinv_safegcd():
     for a in vals:
         assert inv(a) == pow(a, -1, P)
     assert inv(0) == 0      # GPUMath.h:785-793
+
+
+def test_host_fp64_multiplier_is_exact():
+    """kgx_field_fp64.cuh (the DFMA-pipe 256x256 -> 512 multiplier, 52-bit limbs, round-toward-zero FMA splitting): the host
+    twin must reproduce big-integer products exactly, incl. all-ones and limb-boundary operands."""
+    import ctypes
+    import random
+    from kangaroo_b200 import _lib
+    L = ctypes.CDLL(_lib.HOSTTEST_PATH)
+    A, O = ctypes.c_uint64 * 4, ctypes.c_uint64 * 8
+    M = 2**64 - 1
+
+    def mul(a, b, sq=0):
+        o = O()
+        L.kgx_host_mul512_fp64(o, A(*[(a >> (64 * i)) & M for i in range(4)]), A(*[(b >> (64 * i)) & M for i in range(4)]), sq)
+        return sum(int(o[i]) << (64 * i) for i in range(8))
+    random.seed(5)
+    edge = [0, 1, 2**256 - 1, 2**255, 2**52 - 1, 2**52, 2**104 - 1, 2**104, 2**208 - 1, (1 << 256) - (1 << 52), 2**256 - 0x1000003D1]
+    vals = edge + [random.getrandbits(256) for _ in range(1500)]
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        assert mul(a, b) == a * b
+        assert mul(a, a, 1) == a * a
+    for a in edge:
+        for b in edge:
+            assert mul(a, b) == a * b

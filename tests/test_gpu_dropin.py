@@ -53,3 +53,26 @@ def test_solve_in56():
 def test_solve_in64():
     out = run(["-t", "0", "-gpu", "-g", "64,128", os.path.join(GOLD, "in64.txt")], timeout=900)
     assert "5B3F38AF935A3640D158E871CE6E9666DB862636383386EE510F18CCC3BD72EB" in out.upper(), out[-2000:]
+
+
+def test_checkpoint_round_trip_through_reference_work_files(tmp_path):
+    """`-w f -wi N -ws` makes the reference's Thread.cpp:330-335 request a save, SolveKeyGPU calls
+    GPUEngine::GetKangaroos (Kangaroo.cpp:618-626) and Backup.cpp:449-572 writes HEADW + hash table + every kangaroo; `-i f`
+    reads it back (Backup.cpp:291-364) and the search goes on from the saved herd through SetKangaroos.  Everything but the
+    engine is the reference's own code, so passing means the engine's Get/SetKangaroos round trip is exact at full size
+    (4.85 M kangaroos, 466 MB of walks).  Run 1 saves at the first status tick (2 s) and gives up at 25 % of the expected
+    operations (-m); `-wcheck` validates every stored DP (d*G [+P] == x); run 2 resumes from the file and must find the key."""
+    work = str(tmp_path / "k.work")
+    cfg = os.path.join(GOLD, "puzzle110_window72.txt")
+    out1 = ""
+    for attempt in range(3):                                          # a lucky run may solve before the first save
+        out1 = run(["-t", "0", "-gpu", "-d", "14", "-w", work, "-wi", "1000", "-ws", "-m", "0.25", cfg], timeout=600)
+        if os.path.exists(work) and "Aborted" in out1:
+            break
+    assert os.path.exists(work) and "SaveWork" in out1 and "Aborted" in out1, out1[-2000:]
+    assert os.path.getsize(work) > 4849664 * 96                       # the whole default herd is in the file
+    chk = run(["-wcheck", work], timeout=600)
+    assert "[100.000% OK]" in chk and "Wrong" not in chk, chk[-1500:]         # Check.cpp:393-409
+    out2 = run(["-t", "0", "-gpu", "-i", work], timeout=900)
+    assert "FectchKangaroos" in out2 and "kangaroos loaded" in out2, out2[-2000:]
+    assert "35C0D7234DF7DEB0F20CF7062444" in out2.upper(), out2[-2000:]
