@@ -23,5 +23,9 @@ done
 g++ $FLAGS -c "$HERE/GPUEngine_b200.cpp" -o "$OUT/obj_GPUEngine_b200.o" &
 wait
 g++ -o "$OUT/kangaroo_b200" $OBJS "$OUT/obj_GPUEngine_b200.o" -L"$HERE" -lkgx -lpthread -Wl,-rpath,'$ORIGIN/../kangaroo_b200/csrc'
+# end-to-end timing harness through the same class GPUEngine (bench.py's e2e leg): shim + reference SECPK1 only
+SECP_OBJS=$(for f in Int IntMod IntGroup Point SECP256K1 Random; do echo "$OUT/obj_SECPK1_$f.o"; done)
+g++ $FLAGS -o "$OUT/kgx_shim_bench" "$HERE/shim_bench.cpp" "$OUT/obj_GPUEngine_b200.o" $SECP_OBJS "$OUT/obj_Timer.o" \
+    -L"$HERE" -lkgx -lpthread -Wl,-rpath,'$ORIGIN/../kangaroo_b200/csrc'
 rm -f $OUT/obj_*.o
 echo "built $OUT/kangaroo_b200"

@@ -27,6 +27,8 @@ struct kgx_engine {
   uint4* state = nullptr;
   uint4* pre = nullptr;      // streaming mode: prefix-product scratch
   bool streamMode = false;
+  int streamCtas = 2;
+  bool warpInv = true;       // stream kernel: one warp-wide shuffle-butterfly inverse per pass (false: one per thread)
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
   u32* slabPinned = nullptr;
   u32* dp40 = nullptr;       // [count][maxFound x 10 words]: converted records of the last completed launch
@@ -169,7 +171,14 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
       // kangaroos per thread: 128 (the reference's GPU_GRP_SIZE) when the herd fills two CTAs per SM with it; smaller
       // herds get a smaller group so that the grid still covers the chip (one wave of 2 CTAs/SM), at the price of more
       // inversions per jump.  KGX_STREAM_G overrides.
-      const u64 slots = (u64)2 * prop.multiProcessorCount * 128;          // threads of one wave
+      int ctas = 2;
+      if (const char* sc = getenv("KGX_STREAM_CTAS")) ctas = atoi(sc);
+      if (ctas != 2 && ctas != 3) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_CTAS must be 2 or 3"); delete e; return nullptr; }
+      if (const char* si = getenv("KGX_STREAM_INV")) {
+        if (!strcmp(si, "thread")) e->warpInv = false;
+        else if (strcmp(si, "warp")) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_INV must be warp or thread"); delete e; return nullptr; }
+      }
+      const u64 slots = (u64)ctas * prop.multiProcessorCount * 128;       // threads of one wave
       long long g = (long long)((e->n + slots - 1) / slots);               // round UP: never more tiles than one wave
       g = (g + 1) & ~1LL;
       if (g > 128) g = 128;
@@ -177,7 +186,8 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
       if (stream_g > 0) g = stream_g;
       else if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
       if (g < 2 || g > 4096 || (g & 1)) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: stream group size (KGX_STREAM_G) must be an even number in [2, 4096]"); delete e; return nullptr; }
-      e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = 2;
+      e->streamCtas = ctas;
+      e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = ctas;
     }
   }
   const u64 TILE = (u64)e->T * e->K;
@@ -385,7 +395,15 @@ int kgx_launch_async(kgx_engine* e) {
   CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
   u32 grid = (u32)(e->ctasPerSM * e->sms);
   if (grid > e->numTiles) grid = e->numTiles;
-  if (e->streamMode) stream_kernel<128, 2><<<grid, 128, 0, e->stream>>>(p);
+  if (e->streamMode) {
+    if (e->streamCtas == 3) {
+      if (e->warpInv) stream_kernel<128, 3, true><<<grid, 128, 0, e->stream>>>(p);
+      else stream_kernel<128, 3, false><<<grid, 128, 0, e->stream>>>(p);
+    } else {
+      if (e->warpInv) stream_kernel<128, 2, true><<<grid, 128, 0, e->stream>>>(p);
+      else stream_kernel<128, 2, false><<<grid, 128, 0, e->stream>>>(p);
+    }
+  }
   else g_cfgs[e->cfg].kern<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   e->launches++;
   CK(e, cudaGetLastError());

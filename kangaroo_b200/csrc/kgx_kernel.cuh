@@ -271,28 +271,28 @@ __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) 
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
 
-// DP record append (GPUCompute.h:96-105, GPUMath.h:173-188): rare path, kept out of line so the jump loop stays one
-// basic block and ptxas can interleave the two kangaroos of an unrolled pair.
-// (pointer arguments: the caller's rx/d arrays get a local-memory home that is written once per jump with three
-// STL.128; passing the 14 words by value instead costs 17 more registers and measured 2 % slower)
-__device__ __noinline__ void emit_dp(const LaunchParams& p, const u32* rx, const u32* d, u64 kidx) {
+// DP record append (GPUCompute.h:96-105, GPUMath.h:173-188): rare path (2^-dp per jump), kept out of line so the jump loop
+// stays one basic block.  The record is re-read from the kangaroo's own state chunks, which stream_body has just
+// written (same thread, program order): the hot loop keeps neither x' nor d' alive for it -- no local-memory home, no
+// extra registers.
+template <int T>
+__device__ __noinline__ void emit_dp_from_state(const LaunchParams& p, const uint4* sg, u64 kidx) {
   if (kidx >= p.nKangaroos) return;                    // padding slot
   const u32 pos = atomicAdd(p.out, 1u);
   if (pos >= p.maxFound) return;                       // GPUEngine.cu:641-648: counted, not stored
+  const uint4 x0 = sg[0], x1 = sg[T], d = sg[4 * T];
   u32* o = p.out + 1 + (size_t)pos * 14;
-#pragma unroll
-  for (int w = 0; w < 8; w++) o[w] = rx[w];
-  o[8] = d[0]; o[9] = d[1]; o[10] = d[2]; o[11] = d[3];
+  o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
+  o[8] = d.x; o[9] = d.y; o[10] = d.z; o[11] = d.w;
   o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
 }
 
 // One kangaroo of the fused pass (see the file header): back-substitute, jump, start the next chain.  Branch-free:
-// returns whether the new point is distinguished, leaving x' in rx[] and the new distance in d[] for emit_dp.
+// returns whether the new point is distinguished (x' and d' are in the state chunks for emit_dp_from_state).
 template <int T>
 __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, const u32* jpx, const u32* jpy,
-                                            const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi,
-                                            u32* rx, u32* d) {
-  u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], ry[8];
+                                            const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi) {
+  u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8], d[4];
   unpack8(x, cur.x0, cur.x1);
   unpack8(inv, cur.p0, cur.p1);
   const u32 j = x[0] & 31u;
@@ -326,7 +326,28 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
   return ((rx[7] & mhi) | (rx[6] & mlo)) == 0u;          // GPUCompute.h:96
 }
 
-template <int T, int CTAS>
+// Group inverse of the stream kernel.  WARPINV = false: every thread inverts the product of its own G kangaroos (lanes
+// diverge inside the variable-time safegcd).  WARPINV = true: the 32 lane products are multiplied together by an XOR
+// butterfly (5 shuffle rounds, every lane keeps the sibling factor of each round), ONE warp-uniform inverse is computed
+// -- no divergence, 32 x fewer inversions -- and the butterfly is walked back: 10 multiplications per lane per pass buy
+// a Montgomery group of 32*G kangaroos (north_star: "batch-inverse prefix/suffix products done with warp shuffles so one
+// inverse amortises over the whole group").  Same canonical inverses either way.
+template <bool WARPINV>
+__device__ __forceinline__ void stream_group_inverse(u32* I, const u32* P) {
+  if (!WARPINV) { fe_inv(I, P); return; }
+  u32 v[8], sib[5][8];
+  fe_copy(v, P);
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+    shfl_xor_fe(sib[l], v, 1 << l);
+    fe_mul(v, v, sib[l]);
+  }
+  fe_inv(I, v);                                  // identical in all 32 lanes
+#pragma unroll
+  for (int l = 4; l >= 0; l--) fe_mul(I, I, sib[l]);       // -> 1 / (this lane's own product)
+}
+
+template <int T, int CTAS, bool WARPINV>
 __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
   const int G = p.G;     // even: the fused pass is unrolled by two
   __shared__ u32 sJ[JT_WORDS];
@@ -358,7 +379,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
     int backward = 1;
     for (int run = 0; run < p.nRun; run++) {
       u32 I[8];
-      fe_inv(I, P);                              // this thread's own group: 1 / (dx_0 ... dx_{G-1})
+      stream_group_inverse<WARPINV>(I, P);       // 1 / (dx_0 ... dx_{G-1}) of this thread's G kangaroos
       fe_set_one(P);
       const int g0 = backward ? (G - 1) : 0;
       const ptrdiff_t ds = backward ? -(ptrdiff_t)(CHUNKS * T) : (ptrdiff_t)(CHUNKS * T);   // pointer steps per kangaroo
@@ -371,13 +392,12 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
       stream_load<T>(A, sg, pg);
 #pragma unroll 1
       for (int i = 0; i < G; i += 2) {
-        u32 rxa[8], da[4], rxb[8], db[4];
         stream_load<T>(B, sg + ds, pg + dp);
-        const bool ha = stream_body<T>(A, sg, pg, jpx, jpy, jd, I, P, mlo, mhi, rxa, da);
+        const bool ha = stream_body<T>(A, sg, pg, jpx, jpy, jd, I, P, mlo, mhi);
         if (i + 2 < G) stream_load<T>(A, sg + 2 * ds, pg + 2 * dp);
-        const bool hb = stream_body<T>(B, sg + ds, pg + dp, jpx, jpy, jd, I, P, mlo, mhi, rxb, db);
-        if (ha) emit_dp(p, rxa, da, kidx);
-        if (hb) emit_dp(p, rxb, db, kidx + dk);
+        const bool hb = stream_body<T>(B, sg + ds, pg + dp, jpx, jpy, jd, I, P, mlo, mhi);
+        if (ha) emit_dp_from_state<T>(p, sg, kidx);
+        if (hb) emit_dp_from_state<T>(p, sg + ds, kidx + dk);
         sg += 2 * ds; pg += 2 * dp; kidx += 2 * dk;
       }
       backward ^= 1;

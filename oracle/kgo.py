@@ -155,6 +155,45 @@ class _Backend:
         assert cnt <= max_dp, "DP buffer too small"
         return [(from_limbs(dps[i].x), from_limbs(dps[i].d), int(dps[i].kidx), int(dps[i].jump)) for i in range(cnt)]
 
+    # --- USE_SYMMETRY paths (Constants.h:25) ------------------------------------------------------
+    def create_jump_table_sym(self, range_power):
+        """Kangaroo.cpp:742-832, USE_SYMMETRY branch -> (jd, jpx, jpy); self.last_uv = the two primes."""
+        jd = np.zeros((NB_JUMP, 2), dtype=np.uint64)
+        jpx = np.zeros((NB_JUMP, 4), dtype=np.uint64)
+        jpy = np.zeros((NB_JUMP, 4), dtype=np.uint64)
+        uv = np.zeros(2, dtype=np.uint64)
+        f = self._f("create_jump_table_sym"); f.restype = ctypes.c_int
+        self.last_draws = f(ctypes.c_int(range_power), _ptr(jd), _ptr(jpx), _ptr(jpy), _ptr(uv))
+        assert self.last_draws > 0
+        self.last_uv = (int(uv[0]), int(uv[1]))
+        return jd, jpx, jpy
+
+    def create_herd_sym(self, n, range_power, width_div4, key, first_type=0):
+        """Kangaroo.cpp:670-738, USE_SYMMETRY branch -> px, py, d (n,4); y already in the lower half, d sign-switched with it."""
+        px = np.zeros((n, 4), dtype=np.uint64); py = np.zeros((n, 4), dtype=np.uint64)
+        d = np.zeros((n, 4), dtype=np.uint64)
+        self._f("create_herd_sym")(ctypes.c_int(n), ctypes.c_int(range_power), _ptr(to_limbs(width_div4)),
+                                   _ptr(to_limbs(key[0])), _ptr(to_limbs(key[1])), ctypes.c_int(first_type),
+                                   _ptr(px), _ptr(py), _ptr(d))
+        return px, py, d
+
+    def jump_sym(self, px, py, d, last_jump, table, njumps, dp_mask, grp=1024, max_dp=1 << 20):
+        """The symmetric walk of Check.cpp:534-556 (lastJump limiter + class switch), in place; last_jump: uint8 (n,).
+        -> list of (x, d mod n, kidx, jump) DPs."""
+        jd, jpx, jpy = table
+        n = px.shape[0]
+        dps = (DP * max_dp)()
+        f = self._f("jump_sym"); f.restype = ctypes.c_uint64
+        lj = last_jump.ctypes.data_as(ctypes.c_void_p)
+        if self.prefix == "ref_":
+            cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), _ptr(px), _ptr(py), _ptr(d), lj, _ptr(jd), _ptr(jpx), _ptr(jpy),
+                    ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp))
+        else:
+            cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), ctypes.c_int(grp), _ptr(px), _ptr(py), _ptr(d), lj, _ptr(jd), _ptr(jpx),
+                    _ptr(jpy), ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp))
+        assert cnt <= max_dp, "DP buffer too small"
+        return [(from_limbs(dps[i].x), from_limbs(dps[i].d), int(dps[i].kidx), int(dps[i].jump)) for i in range(cnt)]
+
     def jump_single(self, x, y, d, table):
         """Check.cpp:534-549 formulation (one AddDirect per jump). -> (x, y, d)."""
         jd, jpx, jpy = table

@@ -88,6 +88,15 @@ void kgo_hash_convert(const uint64_t x[4], const uint64_t d[4], uint32_t type,
  * each on its own 1024-kangaroo group). Returns total jumps done; seconds in *sec. */
 uint64_t kgo_bench_cpu(int threads, int jumps_per_kangaroo, int range_power, double *sec);
 
+/* ---- USE_SYMMETRY restatement (Constants.h:25; Kangaroo.cpp:742-832, 670-738 sym branches; Check.cpp:534-556) ---- */
+int  kgo_mod_positive(uint64_t y[4]);                                        /* IntMod.cpp:1270-1283 ModPositiveK1 */
+void kgo_order_neg(uint64_t r[4], const uint64_t d[4]);                      /* IntMod.cpp:1265-1268 ModNegK1order */
+int  kgo_create_jump_table_sym(int range_power, uint64_t *jd, uint64_t *jpx, uint64_t *jpy, uint64_t uv[2]);
+void kgo_create_herd_sym(int n, int range_power, const uint64_t range_width_div4[4], const uint64_t keyx[4], const uint64_t keyy[4],
+                         int first_type, uint64_t *px, uint64_t *py, uint64_t *d);
+uint64_t kgo_jump_sym(int n, int njumps, int grp, uint64_t *px, uint64_t *py, uint64_t *d, uint8_t *last_jump,
+                      const uint64_t *jd, const uint64_t *jpx, const uint64_t *jpy, uint64_t dp_mask, kgo_dp_t *dps, uint64_t max_dp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,4 +241,104 @@ uint64_t ref_bench_cpu(int threads, int jumps_per_kangaroo, int rangePower, doub
   return total;
 }
 
+/* ===== USE_SYMMETRY paths (Constants.h:25), driven through the same public reference API =====
+ * The library itself is compiled WITHOUT the macro (SECPK1 / HashTable do not depend on it); the three private Kangaroo
+ * members are re-expressed from their USE_SYMMETRY branches, call for call: CreateJumpTable (Kangaroo.cpp:742-832),
+ * CreateHerd (:670-738) and the symmetric walk as Kangaroo::Check replays it on the CPU (Check.cpp:534-556). */
+int ref_create_jump_table_sym(int rangePower, uint64_t *jd, uint64_t *jpx, uint64_t *jpy, uint64_t uv[2]) {
+  int jumpBit = rangePower / 2;
+  if (jumpBit > 128) jumpBit = 128;
+  int maxRetry = 100; bool ok = false; double distAvg; int draws = 0;
+  double maxAvg = pow(2.0, (double)jumpBit - 0.95);
+  double minAvg = pow(2.0, (double)jumpBit - 1.05);
+  Int jumpDistance[NB_JUMP];
+  rseed(0x600DCAFE);
+  Int old; old.Set(Int::GetFieldCharacteristic());
+  Int u, v;
+  u.SetInt32(1); u.ShiftL(jumpBit / 2); u.AddOne();
+  while (!u.IsProbablePrime()) { u.AddOne(); u.AddOne(); }
+  v.Set(&u); v.AddOne(); v.AddOne();
+  while (!v.IsProbablePrime()) { v.AddOne(); v.AddOne(); }
+  Int::SetupField(&old);
+  if (uv) { uv[0] = u.bits64[0]; uv[1] = v.bits64[0]; }
+  while (!ok && maxRetry > 0) {
+    Int totalDist; totalDist.SetInt32(0);
+    for (int i = 0; i < NB_JUMP / 2; ++i) {
+      jumpDistance[i].Rand(jumpBit / 2); jumpDistance[i].Mult(&u);
+      if (jumpDistance[i].IsZero()) jumpDistance[i].SetInt32(1);
+      totalDist.Add(&jumpDistance[i]);
+    }
+    for (int i = NB_JUMP / 2; i < NB_JUMP; ++i) {
+      jumpDistance[i].Rand(jumpBit / 2); jumpDistance[i].Mult(&v);
+      if (jumpDistance[i].IsZero()) jumpDistance[i].SetInt32(1);
+      totalDist.Add(&jumpDistance[i]);
+    }
+    distAvg = totalDist.ToDouble() / (double)(NB_JUMP);
+    ok = distAvg > minAvg && distAvg < maxAvg;
+    maxRetry--; draws++;
+  }
+  for (int i = 0; i < NB_JUMP; ++i) {
+    Point J = secp->ComputePublicKey(&jumpDistance[i]);
+    from_int(jd + 2 * i, jumpDistance[i], 2);
+    from_int(jpx + 4 * i, J.x); from_int(jpy + 4 * i, J.y);
+  }
+  return draws;
+}
+
+void ref_create_herd_sym(int n, int rangePower, const uint64_t wdiv4[4], const uint64_t keyx[4], const uint64_t keyy[4],
+                         int firstType, uint64_t *px, uint64_t *py, uint64_t *d) {
+  Int W; to_int(W, wdiv4);
+  Int one; one.SetInt32(1);
+  Int KX, KY; to_int(KX, keyx); to_int(KY, keyy);
+  Point key(&KX, &KY, &one);
+  std::vector<Int> pk; std::vector<Point> S, Sp;
+  Point Z; Z.Clear();
+  std::vector<Int> dd(n);
+  for (int j = 0; j < n; j++) {
+    dd[j].Rand(rangePower - 1);                                   /* Tame in [0..N/2] */
+    if ((j + firstType) % 2 == WILD) dd[j].ModSubK1order(&W);     /* Wild in [-N/4..N/4] */
+    pk.push_back(dd[j]);
+  }
+  S = secp->ComputePublicKeys(pk);
+  for (int j = 0; j < n; j++) Sp.push_back(((j + firstType) % 2 == TAME) ? Z : key);
+  S = secp->AddDirect(Sp, S);
+  for (int j = 0; j < n; j++) {
+    Int X, Y; X.Set(&S[j].x); Y.Set(&S[j].y);
+    if (Y.ModPositiveK1()) dd[j].ModNegK1order();                 /* Kangaroo.cpp:730-734 */
+    from_int(px + 4 * j, X); from_int(py + 4 * j, Y); from_int(d + 4 * j, dd[j]);
+  }
+}
+
+/* Check.cpp:534-556 (USE_SYMMETRY): one AddDirect per kangaroo per jump, lastJump cycle limiter, class switch. */
+uint64_t ref_jump_sym(int n, int njumps, uint64_t *px, uint64_t *py, uint64_t *d, uint8_t *lastJump,
+                      const uint64_t *jd, const uint64_t *jpx, const uint64_t *jpy, uint64_t dMask, ref_dp_t *dps, uint64_t max_dp) {
+  Int one; one.SetInt32(1);
+  Int jD[NB_JUMP], jPx[NB_JUMP], jPy[NB_JUMP];
+  for (int i = 0; i < NB_JUMP; i++) { to_int(jD[i], jd + 2 * i, 2); to_int(jPx[i], jpx + 4 * i); to_int(jPy[i], jpy + 4 * i); }
+  uint64_t ndp = 0;
+  for (int r = 0; r < njumps; r++) {
+    for (int i = 0; i < n; i++) {
+      Int X, Y, D; to_int(X, px + 4 * i); to_int(Y, py + 4 * i); to_int(D, d + 4 * i);
+      uint64_t jmp = (X.bits64[0] % NB_JUMP);
+      if (jmp == lastJump[i]) jmp = (lastJump[i] + 1) % NB_JUMP;
+      Point J(&jPx[jmp], &jPy[jmp], &one);
+      Point P(&X, &Y, &one);
+      P = secp->AddDirect(P, J);
+      X.Set(&P.x); Y.Set(&P.y);
+      D.ModAddK1order(&jD[jmp]);
+      if (Y.ModPositiveK1()) D.ModNegK1order();
+      lastJump[i] = (uint8_t)jmp;
+      from_int(px + 4 * i, X); from_int(py + 4 * i, Y); from_int(d + 4 * i, D);
+      if ((X.bits64[3] & dMask) == 0) {
+        if (dps && ndp < max_dp) {
+          from_int(dps[ndp].x, X); from_int(dps[ndp].d, D);
+          dps[ndp].kidx = (uint64_t)i; dps[ndp].jump = (uint32_t)(r + 1); dps[ndp].pad = 0;
+        }
+        ndp++;
+      }
+    }
+  }
+  return ndp;
+}
+
 } /* extern "C" */

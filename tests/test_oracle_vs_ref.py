@@ -3,6 +3,7 @@
 import random
 
 import numpy as np
+import pytest
 
 from oracle import kgo
 
@@ -88,3 +89,51 @@ def test_hash_convert(oracle, reference):
         d = rng.randrange(2**126) if rng.random() < 0.5 else N - rng.randrange(1, 2**126)
         t = rng.randrange(2)
         assert oracle.hash_convert(x, d, t) == reference.hash_convert(x, d, t)
+
+
+# ---- USE_SYMMETRY restatement pinned to the reference's own Int / Secp256K1 code -------------------------
+@pytest.mark.parametrize("rp", [40, 56, 64, 80, 109, 125])
+def test_symmetric_jump_table_matches_reference(oracle, reference, rp):
+    """Kangaroo.cpp:742-832 USE_SYMMETRY branch: the two primes u, v come from Int::IsProbablePrime, whose Miller-Rabin bases
+    are drawn from the same MT19937 stream as the distances -- the oracle reproduces that consumption exactly."""
+    a = oracle.create_jump_table_sym(rp)
+    b = reference.create_jump_table_sym(rp)
+    assert oracle.last_uv == reference.last_uv and oracle.last_draws == reference.last_draws
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    jd = a[0]
+    u, v = oracle.last_uv
+    assert all(int(jd[i, 0]) % u == 0 for i in range(16)) and all(int(jd[i, 0]) % v == 0 for i in range(16, 32))
+
+
+def test_symmetric_herd_and_walk_match_reference(oracle, reference):
+    """CreateHerd (Kangaroo.cpp:670-738, sym branch) and the symmetric walk Check.cpp:534-556 replays (lastJump limiter,
+    ModPositiveK1 class switch, d = n - d): oracle (batched inverse) == reference (one AddDirect per jump), bit for bit."""
+    rp = 64
+    key = oracle.ec_mul_g(0x5B3F38AF935A3640D158E871CE6E9666DB862636383386EE0000000000123000)
+    wdiv4 = ((1 << rp) - 1) >> 2
+    table = oracle.create_jump_table_sym(rp)
+    n = 96
+    for be in (oracle, reference):
+        be.rseed(777)
+    ox, oy, od = oracle.create_herd_sym(n, rp, wdiv4, key, 0)
+    rx, ry, rd = reference.create_herd_sym(n, rp, wdiv4, key, 0)
+    assert np.array_equal(ox, rx) and np.array_equal(oy, ry) and np.array_equal(od, rd)
+    half = (kgo.P - 1) // 2
+    assert all(kgo.from_limbs(oy[i]) <= half for i in range(n))
+    assert any(kgo.from_limbs(od[i]) > kgo.N // 2 for i in range(n))           # some distances went negative (mod n)
+    lo, lr = np.full(n, 32, dtype=np.uint8), np.full(n, 32, dtype=np.uint8)
+    mask = oracle.dp_mask(4)
+    do = oracle.jump_sym(ox, oy, od, lo, table, 200, mask, grp=32)
+    dr = reference.jump_sym(rx, ry, rd, lr, table, 200, mask)
+    assert np.array_equal(ox, rx) and np.array_equal(oy, ry) and np.array_equal(od, rd) and np.array_equal(lo, lr)
+    assert sorted(do) == sorted(dr) and len(do) > 500
+    # invariant of the class walk: tame x == (d*G).x ; wild x == (key + d*G).x or (key - d*G).x -- a class switch negates
+    # the whole point, i.e. d AND the key term, which is why CheckKey tries +-key and the four sign pairs (Kangaroo.cpp:218-253)
+    for i in (0, 1, 2, 3, 50, 95):
+        dv = kgo.from_limbs(od[i])
+        if i % 2 == 0:
+            assert oracle.ec_mul_g(dv)[0] == kgo.from_limbs(ox[i])
+        else:
+            cands = (oracle.ec_add(key, oracle.ec_mul_g(dv))[0], oracle.ec_add(key, oracle.ec_mul_g(N - dv))[0])
+            assert kgo.from_limbs(ox[i]) in cands
