@@ -232,7 +232,8 @@ def shim_prepare(eng, case, sc, local_rank):
     tmp = tempfile.mkdtemp(prefix="kgx_shim_%d_" % local_rank)
     tab_path, herd_path = os.path.join(tmp, "table.bin"), os.path.join(tmp, "herd.bin")
     jd, jpx, jpy = case["table"]
-    tab = np.concatenate([_limb_rows(jd, 2), _limb_rows(jpx, 4), _limb_rows(jpy, 4)], axis=1)        # 32 x 10
+    as_rows = lambda a, limbs: (np.ascontiguousarray(a, dtype=np.uint64)[:, :limbs] if isinstance(a, np.ndarray) else _limb_rows(a, limbs))
+    tab = np.concatenate([as_rows(jd, 2), as_rows(jpx, 4), as_rows(jpy, 4)], axis=1)                 # 32 x 10
     with open(tab_path, "wb") as f:
         f.write(tab.tobytes()); f.write(_limb_rows([case["width_div2"]], 4).tobytes())
     np.concatenate([ax, ay, np.ascontiguousarray(sc, dtype=np.uint64)], axis=1).tofile(herd_path)   # n x 12

@@ -61,6 +61,16 @@ const char* kgx_last_error(kgx_engine* e);      /* e may be NULL: error of the l
 uint64_t    kgx_num_kangaroos(kgx_engine* e);   /* groups * threads_per_group * 128 */
 uint64_t    kgx_memory_bytes(kgx_engine* e);    /* device bytes held (GPUEngine::GetMemory) */
 
+/* --- USE_SYMMETRY engine mode (reference: compile-time switch Constants.h:25; device side GPUCompute.h:27-60, 91-94,
+ *     GPUMath.h:518-547; parity definition Check.cpp:534-556).  on != 0: every jump uses the lastJump 2-cycle limiter and the
+ *     equivalence-class switch (y > (p-1)/2 -> point negated, distance negated).  Distances crossing this ABI (upload,
+ *     download, patch, create_herd, DP items) are then SIGNED 128-bit two's complement values and NO wild offset is applied
+ *     (the reference's biased-unsigned device form cannot represent the sign changes: its ModNeg256Order writes 256 bits
+ *     into a 128-bit slot).  lastJump is reset to "none" by upload / patch / create_herd like GPUEngine.cu:413-416, 532-536.
+ *     Call before the herd is uploaded. --- */
+int kgx_set_symmetry(kgx_engine* e, int on);
+int kgx_get_symmetry(kgx_engine* e);
+
 /* --- GPUEngine::SetParams (GPUEngine.cu:559-590): jd 32x2, jpx/jpy 32x4 limbs --- */
 int kgx_set_params(kgx_engine* e, uint64_t dp_mask, const uint64_t* jd, const uint64_t* jpx, const uint64_t* jpy);
 

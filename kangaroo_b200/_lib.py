@@ -30,6 +30,8 @@ _SIGS = {
     "kgx_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "kgx_num_kangaroos": (ctypes.c_uint64, [ctypes.c_void_p]),
     "kgx_memory_bytes": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "kgx_set_symmetry": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "kgx_get_symmetry": (ctypes.c_int, [ctypes.c_void_p]),
     "kgx_set_params": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _u64p, _u64p, _u64p]),
     "kgx_upload": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, _u64p]),
     "kgx_download": (ctypes.c_int, [ctypes.c_void_p, _u64p, _u64p, _u64p]),

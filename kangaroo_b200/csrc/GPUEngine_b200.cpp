@@ -18,6 +18,42 @@
 
 static void int_to_limbs(uint64_t* dst, Int* v, int limbs) { for (int i = 0; i < limbs; i++) dst[i] = v->bits64[i]; }
 
+// Distance marshalling across the C ABI.
+//   default build : the reference's convention -- wild (odd kIdx) distances biased by wildOffset mod n on the way in and
+//                   un-biased on the way out (GPUEngine.cu:407-411, 477, 526, 672), 128 bits unsigned on the device.
+//   USE_SYMMETRY  : the engine is switched to kgx_set_symmetry(1); distances change sign on the device, so they travel as
+//                   SIGNED 128-bit values: d mod n above n/2 is negative (the same test HashTable::Convert uses,
+//                   HashTable.cpp:84-92).  The wild offset the host passes (rangeWidthDiv4, Kangaroo.cpp:548-550) is not
+//                   applied: with sign switches a bias does not commute with negation, which is one of the reasons the
+//                   reference's own symmetric GPU path cannot pass its `-check` (symmetry).
+static void dist_to_abi(uint64_t dst[2], Int* d, bool wild, Int* wildOffset) {
+#ifdef USE_SYMMETRY
+  (void)wild; (void)wildOffset;
+  if (d->bits64[3] > 0x7FFFFFFFFFFFFFFFULL) {
+    Int t; t.Set(d); t.ModNegK1order();                       // |d|
+    dst[0] = ~t.bits64[0] + 1; dst[1] = ~t.bits64[1] + (dst[0] == 0 ? 1 : 0);
+  } else { dst[0] = d->bits64[0]; dst[1] = d->bits64[1]; }
+#else
+  Int dOff; dOff.Set(d);
+  if (wild) dOff.ModAddK1order(wildOffset);
+  dst[0] = dOff.bits64[0]; dst[1] = dOff.bits64[1];
+#endif
+}
+static void dist_from_abi(Int* d, const uint64_t src[2], bool wild, Int* wildOffset) {
+  d->SetInt32(0);
+#ifdef USE_SYMMETRY
+  (void)wild; (void)wildOffset;
+  if (src[1] >> 63) {
+    uint64_t m0 = ~src[0] + 1, m1 = ~src[1] + (m0 == 0 ? 1 : 0);
+    d->bits64[0] = m0; d->bits64[1] = m1;
+    d->ModNegK1order();
+  } else { d->bits64[0] = src[0]; d->bits64[1] = src[1]; }
+#else
+  d->bits64[0] = src[0]; d->bits64[1] = src[1];
+  if (wild) d->ModSubK1order(wildOffset);
+#endif
+}
+
 void GPUEngine::SetWildOffset(Int* offset) { wildOffset.Set(offset); }        // GPUEngine.cu:140-142
 
 GPUEngine::GPUEngine(int nbThreadGroup, int nbThreadPerGroup, int gpuId, uint32_t maxFound) {   // GPUEngine.cu:144-253
@@ -32,6 +68,9 @@ GPUEngine::GPUEngine(int nbThreadGroup, int nbThreadPerGroup, int gpuId, uint32_
   kgx_engine* e = kgx_create(gpuId, nbThreadGroup, nbThreadPerGroup, maxFound);
   if (!e) { printf("GPUEngine: %s\n", kgx_last_error(NULL)); return; }        // callers never check (Kangaroo.cpp:523-526)
   inputKangaroo = reinterpret_cast<uint64_t*>(e);
+#ifdef USE_SYMMETRY
+  if (kgx_set_symmetry(e, 1) != 0) { printf("GPUEngine: %s\n", kgx_last_error(e)); kgx_destroy(e); inputKangaroo = NULL; return; }
+#endif
   outputItemPinned = reinterpret_cast<uint32_t*>(new kgx_item[maxFound]);
   kangarooSize = (uint32_t)kgx_memory_bytes(e);
   char info[256] = "", name[200] = "?"; int sms = 0;
@@ -89,9 +128,7 @@ void GPUEngine::SetKangaroos(Int* px, Int* py, Int* d) {                        
   std::vector<uint64_t> ax(n * 4), ay(n * 4), ad(n * 2);
   for (uint64_t i = 0; i < n; i++) {
     int_to_limbs(&ax[4 * i], &px[i], 4); int_to_limbs(&ay[4 * i], &py[i], 4);
-    Int dOff; dOff.Set(&d[i]);
-    if (i % 2 == WILD) dOff.ModAddK1order(&wildOffset);
-    ad[2 * i] = dOff.bits64[0]; ad[2 * i + 1] = dOff.bits64[1];
+    dist_to_abi(&ad[2 * i], &d[i], i % 2 == WILD, &wildOffset);
   }
   if (kgx_upload(KGX(inputKangaroo), ax.data(), ay.data(), ad.data()) != 0) printf("GPUEngine: SetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo)));
 }
@@ -104,10 +141,7 @@ void GPUEngine::GetKangaroos(Int* px, Int* py, Int* d) {                        
   for (uint64_t i = 0; i < n; i++) {
     for (int k = 0; k < 4; k++) { px[i].bits64[k] = ax[4 * i + k]; py[i].bits64[k] = ay[4 * i + k]; }
     px[i].bits64[4] = 0; py[i].bits64[4] = 0;
-    Int dOff; dOff.SetInt32(0);
-    dOff.bits64[0] = ad[2 * i]; dOff.bits64[1] = ad[2 * i + 1];
-    if (i % 2 == WILD) dOff.ModSubK1order(&wildOffset);
-    d[i].Set(&dOff);
+    dist_from_abi(&d[i], &ad[2 * i], i % 2 == WILD, &wildOffset);
   }
 }
 
@@ -115,9 +149,7 @@ void GPUEngine::SetKangaroo(uint64_t kIdx, Int* px, Int* py, Int* d) {          
   if (!inputKangaroo) return;
   uint64_t x[4], y[4], dd[2];
   int_to_limbs(x, px, 4); int_to_limbs(y, py, 4);
-  Int dOff; dOff.Set(d);
-  if (kIdx % 2 == WILD) dOff.ModAddK1order(&wildOffset);
-  dd[0] = dOff.bits64[0]; dd[1] = dOff.bits64[1];
+  dist_to_abi(dd, d, kIdx % 2 == WILD, &wildOffset);
   if (kgx_patch(KGX(inputKangaroo), kIdx, x, y, dd) != 0) printf("GPUEngine: SetKangaroo: %s\n", kgx_last_error(KGX(inputKangaroo)));
 }
 
@@ -161,9 +193,7 @@ bool GPUEngine::Launch(std::vector<ITEM>& hashFound, bool spinWait) {           
     it.kIdx = items[i].kidx;
     for (int k = 0; k < 4; k++) it.x.bits64[k] = items[i].x[k];
     it.x.bits64[4] = 0;
-    it.d.bits64[0] = items[i].d[0]; it.d.bits64[1] = items[i].d[1];
-    it.d.bits64[2] = 0; it.d.bits64[3] = 0; it.d.bits64[4] = 0;
-    if (it.kIdx % 2 == WILD) it.d.ModSubK1order(&wildOffset);
+    dist_from_abi(&it.d, items[i].d, it.kIdx % 2 == WILD, &wildOffset);
     hashFound.push_back(it);
   }
   return true;

@@ -28,6 +28,8 @@ struct kgx_engine {
   uint4* pre = nullptr;      // streaming mode: prefix-product scratch
   bool streamMode = false;
   int streamCtas = 2;
+  bool symmetry = false;     // USE_SYMMETRY engine mode (kgx_set_symmetry): lastJump limiter + class switch, signed distances
+  uint8_t* aux = nullptr;    // symmetric mode: lastJump per slot
   bool warpInv = true;       // stream kernel: one warp-wide shuffle-butterfly inverse per pass (false: one per thread)
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
   u32* slabPinned = nullptr;
@@ -60,10 +62,12 @@ struct kgx_engine {
   } while (0)
 
 // Tile geometries compiled in.  The default was picked by the sweep recorded in profiles/ (KGX_CFG="T,K" overrides).
-struct CfgEntry { int T, K, smem, ctas; void (*kern)(LaunchParams); };
-#define KGX_CFG_ENTRY(T_, K_) { T_, K_, Cfg<T_, K_>::SMEM_BYTES, Cfg<T_, K_>::CTAS_PER_SM, jump_kernel<T_, K_> }
+// kernSym: the symmetric-mode (USE_SYMMETRY) instantiation; only the default geometry carries one (others: NULL).
+struct CfgEntry { int T, K, smem, ctas; void (*kern)(LaunchParams); void (*kernSym)(LaunchParams); };
+#define KGX_CFG_ENTRY(T_, K_) { T_, K_, Cfg<T_, K_>::SMEM_BYTES, Cfg<T_, K_>::CTAS_PER_SM, jump_kernel<T_, K_, false>, nullptr }
+#define KGX_CFG_ENTRY_SYM(T_, K_) { T_, K_, Cfg<T_, K_>::SMEM_BYTES, Cfg<T_, K_>::CTAS_PER_SM, jump_kernel<T_, K_, false>, jump_kernel<T_, K_, true> }
 static const CfgEntry g_cfgs[] = {
-  KGX_CFG_ENTRY(128, 7), KGX_CFG_ENTRY(128, 4), KGX_CFG_ENTRY(128, 5), KGX_CFG_ENTRY(64, 7), KGX_CFG_ENTRY(64, 5),
+  KGX_CFG_ENTRY_SYM(128, 7), KGX_CFG_ENTRY(128, 4), KGX_CFG_ENTRY(128, 5), KGX_CFG_ENTRY(64, 7), KGX_CFG_ENTRY(64, 5),
   KGX_CFG_ENTRY(64, 6), KGX_CFG_ENTRY(64, 4), KGX_CFG_ENTRY(96, 6), KGX_CFG_ENTRY(256, 3), KGX_CFG_ENTRY(32, 8), KGX_CFG_ENTRY(32, 12),
 };
 static const int g_ncfg = sizeof(g_cfgs) / sizeof(g_cfgs[0]);
@@ -108,7 +112,7 @@ void kgx_destroy(kgx_engine* e) {
   cudaSetDevice(e->dev);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->dp40); cudaFree(e->herdTab); cudaFree(e->state); cudaFree(e->pre); cudaFree(e->slab[0]); cudaFree(e->slab[1]); cudaFree(e->jtab);
-  cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD);
+  cudaFree(e->stgX); cudaFree(e->stgY); cudaFree(e->stgD); cudaFree(e->aux);
   if (e->slabPinned) cudaFreeHost(e->slabPinned);
   for (int i = 0; i < 2; i++) { if (e->evStart[i]) cudaEventDestroy(e->evStart[i]); if (e->evStop[i]) cudaEventDestroy(e->evStop[i]); }
   if (e->evSnap) cudaEventDestroy(e->evSnap);
@@ -174,7 +178,9 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
       int ctas = 2;
       if (const char* sc = getenv("KGX_STREAM_CTAS")) ctas = atoi(sc);
       if (ctas != 2 && ctas != 3) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_CTAS must be 2 or 3"); delete e; return nullptr; }
+      bool invChosen = false;
       if (const char* si = getenv("KGX_STREAM_INV")) {
+        invChosen = true;
         if (!strcmp(si, "thread")) e->warpInv = false;
         else if (strcmp(si, "warp")) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_STREAM_INV must be warp or thread"); delete e; return nullptr; }
       }
@@ -186,6 +192,10 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
       if (stream_g > 0) g = stream_g;
       else if (const char* sg = getenv("KGX_STREAM_G")) g = atoi(sg);
       if (g < 2 || g > 4096 || (g & 1)) { snprintf(g_create_err, sizeof g_create_err, "kgx_create: stream group size (KGX_STREAM_G) must be an even number in [2, 4096]"); delete e; return nullptr; }
+      // group inverse: the warp-wide shuffle butterfly (one uniform inverse per warp and pass) for long groups, one inverse per
+      // thread for short ones, where the butterfly's 10 extra multiplications per lane weigh more than lane divergence inside
+      // the variable-time inverse -- measured equal at G = 128 (14.16 vs 14.23 GJump/s), 3 % apart at G = 28 (profiles/r2b_sweep.txt)
+      if (!invChosen) e->warpInv = g >= 64;
       e->streamCtas = ctas;
       e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = ctas;
     }
@@ -240,6 +250,29 @@ int kgx_set_jumps_per_launch(kgx_engine* e, int n_run) {
   e->nRun = n_run; return 0;
 }
 
+// USE_SYMMETRY engine mode.  Must be chosen before the herd is uploaded: it allocates the lastJump bytes,
+// switches the jump kernels to their symmetric instantiation and makes every distance crossing the ABI a SIGNED 128-bit
+// two's complement value (no wild-offset bias).
+int kgx_set_symmetry(kgx_engine* e, int on) {
+  CK(e, cudaSetDevice(e->dev));
+  if (e->inflight) { snprintf(e->err, sizeof e->err, "kgx_set_symmetry: a launch is in flight"); return -1; }
+  if (on && !e->streamMode && !g_cfgs[e->cfg].kernSym) {
+    snprintf(e->err, sizeof e->err, "kgx_set_symmetry: tile geometry %d,%d has no symmetric instantiation", e->T, e->K); return -1;
+  }
+  if (on && e->streamMode && e->streamCtas != 2) {
+    snprintf(e->err, sizeof e->err, "kgx_set_symmetry: the symmetric stream kernel is the 2-CTA variant only"); return -1;
+  }
+  if (on && !e->aux) {
+    CK(e, cudaMalloc(&e->aux, e->nPadded));
+    CK(e, cudaMemsetAsync(e->aux, 32, e->nPadded, e->stream));
+  }
+  if (on && !e->streamMode)
+    CK(e, cudaFuncSetAttribute(g_cfgs[e->cfg].kernSym, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smemBytes));
+  e->symmetry = on != 0;
+  return 0;
+}
+int kgx_get_symmetry(kgx_engine* e) { return e->symmetry ? 1 : 0; }
+
 int kgx_set_params(kgx_engine* e, uint64_t dp_mask, const uint64_t* jd, const uint64_t* jpx, const uint64_t* jpy) {
   CK(e, cudaSetDevice(e->dev));
   u32 tab[JT_WORDS];
@@ -277,7 +310,7 @@ int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint
   CK(e, cudaMemcpyAsync(e->stgY, py, e->n * 32, cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaMemcpyAsync(e->stgD, d, e->n * 16, cudaMemcpyHostToDevice, e->stream));
   u32 blocks = (u32)((e->nPadded + 255) / 256);
-  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K);
+  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K, e->aux);
   e->launches++;
   CK(e, cudaGetLastError());
   CK(e, cudaStreamSynchronize(e->stream));
@@ -337,7 +370,7 @@ int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t
   if (kidx >= e->n) { snprintf(e->err, sizeof e->err, "kgx_patch: kidx out of range"); return -1; }
   PatchArgs a;
   memcpy(&a.c[0], px, 32); memcpy(&a.c[2], py, 32); memcpy(&a.c[4], d, 16);
-  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a, e->T, e->K);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
+  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a, e->T, e->K, e->aux);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
   e->launches++;
   CK(e, cudaGetLastError());
   // padding slots replicate kangaroo (s % n): keep them walking their stale copy -- harmless, their DPs are dropped.
@@ -367,11 +400,12 @@ int kgx_create_herd(kgx_engine* e, const uint64_t* scalars, const uint64_t* d128
     CK(e, cudaMemcpyAsync(dKey, key, 64, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemcpyAsync(e->stgD, d128, e->n * 16, cudaMemcpyHostToDevice, e->stream));
     herd_kernel<<<(u32)((e->n + 127) / 128), 128, 0, e->stream>>>(e->herdTab, dScal, dKey, first_type, e->n,
-                                                                 reinterpret_cast<u32*>(e->stgX), reinterpret_cast<u32*>(e->stgY));
+                                                                 reinterpret_cast<u32*>(e->stgX), reinterpret_cast<u32*>(e->stgY),
+                                                                 e->symmetry ? 1 : 0, reinterpret_cast<u32*>(e->stgD));
     e->launches++;
     CK(e, cudaGetLastError());
     u32 blocks = (u32)((e->nPadded + 255) / 256);
-    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K);
+    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K, e->aux);
     e->launches++;
     CK(e, cudaGetLastError());
     CK(e, cudaStreamSynchronize(e->stream));
@@ -390,20 +424,22 @@ int kgx_launch_async(kgx_engine* e) {
   int sidx = e->cur ^ 1;
   LaunchParams p;
   p.state = e->state; p.jtab = e->jtab; p.out = e->slab[sidx]; p.dpMask = e->dpMask; p.nKangaroos = e->n;
-  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre; p.G = e->K;
+  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre; p.G = e->K; p.aux = e->aux;
   CK(e, cudaMemsetAsync(e->slab[sidx], 0, 4, e->stream));            // GPUEngine.cu:543
   CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
   u32 grid = (u32)(e->ctasPerSM * e->sms);
   if (grid > e->numTiles) grid = e->numTiles;
   if (e->streamMode) {
-    if (e->streamCtas == 3) {
-      if (e->warpInv) stream_kernel<128, 3, true><<<grid, 128, 0, e->stream>>>(p);
-      else stream_kernel<128, 3, false><<<grid, 128, 0, e->stream>>>(p);
+    if (e->symmetry) stream_kernel<128, 2, true, true><<<grid, 128, 0, e->stream>>>(p);
+    else if (e->streamCtas == 3) {
+      if (e->warpInv) stream_kernel<128, 3, true, false><<<grid, 128, 0, e->stream>>>(p);
+      else stream_kernel<128, 3, false, false><<<grid, 128, 0, e->stream>>>(p);
     } else {
-      if (e->warpInv) stream_kernel<128, 2, true><<<grid, 128, 0, e->stream>>>(p);
-      else stream_kernel<128, 2, false><<<grid, 128, 0, e->stream>>>(p);
+      if (e->warpInv) stream_kernel<128, 2, true, false><<<grid, 128, 0, e->stream>>>(p);
+      else stream_kernel<128, 2, false, false><<<grid, 128, 0, e->stream>>>(p);
     }
   }
+  else if (e->symmetry) g_cfgs[e->cfg].kernSym<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   else g_cfgs[e->cfg].kern<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   e->launches++;
   CK(e, cudaGetLastError());
@@ -464,7 +500,7 @@ int kgx_convert_dps(kgx_engine* e, const uint64_t wild_offset[2], void** out) {
   CK(e, cudaSetDevice(e->dev));
   if (!e->dp40) CK(e, cudaMalloc(&e->dp40, (size_t)e->maxFound * 40 + 4));
   const int sidx = e->done >= 0 ? e->done : e->cur;
-  dp_convert_kernel<<<64, 256, 0, e->copyStream>>>(e->slab[sidx], e->dp40, e->maxFound, wild_offset[0], wild_offset[1]);
+  dp_convert_kernel<<<64, 256, 0, e->copyStream>>>(e->slab[sidx], e->dp40, e->maxFound, wild_offset[0], wild_offset[1], e->symmetry ? 1 : 0);
   e->launches++;
   CK(e, cudaGetLastError());
   CK(e, cudaStreamSynchronize(e->copyStream));

@@ -255,6 +255,56 @@ __device__ __forceinline__ void d128_add(u32* d, u32 j0, u32 j1, u32 j2, u32 j3)
       : "r"(j0), "r"(j1), "r"(j2), "r"(j3));
 }
 
+// ---- USE_SYMMETRY helpers (reference: Int::ModPositiveK1 IntMod.cpp:1270-1283, GPUMath.h:518-531) ----
+// mask = 0xFFFFFFFF when y > (p-1)/2 (the reference CPU test: 2y - p >= 0), else 0.  (p-1)/2 = 2^255 - 0x800001E9.
+__device__ __forceinline__ u32 fe_gt_half_mask(const u32* y) {
+  u32 t, m;
+  asm("{\n\t"
+      ".reg .u32 t;\n\t"
+      "sub.cc.u32  t, 0x7FFFFE17, %1;\n\t"
+      "subc.cc.u32 t, 0xFFFFFFFF, %2;\n\t"
+      "subc.cc.u32 t, 0xFFFFFFFF, %3;\n\t"
+      "subc.cc.u32 t, 0xFFFFFFFF, %4;\n\t"
+      "subc.cc.u32 t, 0xFFFFFFFF, %5;\n\t"
+      "subc.cc.u32 t, 0xFFFFFFFF, %6;\n\t"
+      "subc.cc.u32 t, 0xFFFFFFFF, %7;\n\t"
+      "subc.cc.u32 t, 0x7FFFFFFF, %8;\n\t"
+      "subc.u32    %0, 0, 0;\n\t"
+      "}"
+      : "=r"(m)
+      : "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
+  (void)t;
+  return m;      // borrow -> 0xFFFFFFFF
+}
+// y = mask ? p - y : y   (p - y = ~y - 0x1000003D0 for y <= p)
+__device__ __forceinline__ void fe_cneg(u32* y, u32 m) {
+  u32 k0 = m & 0x3D0u, k1 = m & 1u;
+  u32 t0 = y[0] ^ m, t1 = y[1] ^ m, t2 = y[2] ^ m, t3 = y[3] ^ m, t4 = y[4] ^ m, t5 = y[5] ^ m, t6 = y[6] ^ m, t7 = y[7] ^ m;
+  asm("sub.cc.u32  %0, %0, %8;\n\t"
+      "subc.cc.u32 %1, %1, %9;\n\t"
+      "subc.cc.u32 %2, %2, 0;\n\t"
+      "subc.cc.u32 %3, %3, 0;\n\t"
+      "subc.cc.u32 %4, %4, 0;\n\t"
+      "subc.cc.u32 %5, %5, 0;\n\t"
+      "subc.cc.u32 %6, %6, 0;\n\t"
+      "subc.u32    %7, %7, 0;"
+      : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7)
+      : "r"(k0), "r"(k1));
+  y[0] = t0; y[1] = t1; y[2] = t2; y[3] = t3; y[4] = t4; y[5] = t5; y[6] = t6; y[7] = t7;
+}
+// signed 128-bit distance: d = mask ? -d : d  (two's complement; the symmetric engine keeps distances signed instead of the
+// reference's biased-unsigned form, whose ModNeg256Order writes 256 bits into a 128-bit slot, GPUMath.h:533-547)
+__device__ __forceinline__ void d128_cneg(u32* d, u32 m) {
+  u32 t0 = d[0] ^ m, t1 = d[1] ^ m, t2 = d[2] ^ m, t3 = d[3] ^ m;
+  asm("sub.cc.u32  %0, %0, %4;\n\t"
+      "subc.cc.u32 %1, %1, %4;\n\t"
+      "subc.cc.u32 %2, %2, %4;\n\t"
+      "subc.u32    %3, %3, %4;"
+      : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3)
+      : "r"(m));
+  d[0] = t0; d[1] = t1; d[2] = t2; d[3] = t3;
+}
+
 __device__ __forceinline__ void fe_copy(u32* r, const u32* a) {
 #pragma unroll
   for (int i = 0; i < 8; i++) r[i] = a[i];

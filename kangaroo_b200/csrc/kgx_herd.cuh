@@ -50,8 +50,10 @@ __global__ void herd_table_kernel(u32* tab) {
 
 // One thread per kangaroo: (x,y) = d*G [+ key].  scal: n x 8 words (d mod group order), key: 16 words or NULL rows
 // where isWild[i]==0.  Writes AoS px,py (n x 8 words each) in kIdx order.
+// sym != 0 (USE_SYMMETRY herd, Kangaroo.cpp:730-734): a point whose y is in the upper half is replaced by its negative and
+// the stored (signed 128-bit) distance dist[i] is negated with it.
 __global__ void herd_kernel(const u32* __restrict__ tab, const u32* __restrict__ scal, const u32* __restrict__ key,
-                            int firstType, u64 n, u32* px, u32* py) {
+                            int firstType, u64 n, u32* px, u32* py, int sym, u32* dist) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   u32 k[8];
@@ -140,6 +142,13 @@ __global__ void herd_kernel(const u32* __restrict__ tab, const u32* __restrict__
       acc = (u64)V[1] + 1u + (acc >> 32); V[1] = (u32)acc;
       for (int w = 2; w < 8; w++) { acc = (u64)V[w] + (acc >> 32); V[w] = (u32)acc; }
     }
+  }
+  if (sym) {
+    const u32 neg = fe_gt_half_mask(Y);
+    fe_cneg(Y, neg);
+    u32 d[4] = {dist[i * 4], dist[i * 4 + 1], dist[i * 4 + 2], dist[i * 4 + 3]};
+    d128_cneg(d, neg);
+    dist[i * 4] = d[0]; dist[i * 4 + 1] = d[1]; dist[i * 4 + 2] = d[2]; dist[i * 4 + 3] = d[3];
   }
 #pragma unroll
   for (int w = 0; w < 8; w++) { px[i * 8 + w] = X[w]; py[i * 8 + w] = Y[w]; }

@@ -38,7 +38,8 @@ struct Cfg {
   static constexpr int S_D = S_P + K * 2 * T;
   static constexpr int S_TOT = S_D + K * T;
   static constexpr int S_JT = S_TOT + 2 * T;
-  static constexpr int SMEM_BYTES = S_JT * 16 + JT_WORDS * 4;
+  static constexpr int LJ_OFF = S_JT * 16 + JT_WORDS * 4;          // symmetric mode: lastJump bytes [K][T]
+  static constexpr int SMEM_BYTES = LJ_OFF + K * T;
   static constexpr int CTAS_PER_SM = (227 * 1024) / (SMEM_BYTES + 1024);
 };
 
@@ -53,6 +54,7 @@ struct LaunchParams {
   int nRun;
   uint4* pre;            // streaming kernel only: prefix-product scratch [numTiles][G][2][T]
   int G;                 // streaming kernel only: kangaroos per thread (even, chosen by the engine from the herd size)
+  uint8_t* aux;          // symmetric mode only: lastJump per kangaroo, [numTiles][G or K][T] bytes (32 = none yet)
   unsigned long long* prof;   // optional: [0]=sum serial cycles, [1]=sum modinv cycles, [2]=sum parallel cycles, [3]=tile-steps (warp 0 of every CTA)
 };
 
@@ -74,6 +76,16 @@ __device__ __forceinline__ void shfl_xor_fe(u32* r, const u32* a, int mask) {
 }
 
 __device__ __forceinline__ void fe_inv(u32* r, const u32* a) { modinv256(r, a); }
+
+// USE_SYMMETRY jump selection as the reference's parity test defines it across the GPUEngine boundary (Check.cpp:536-541 ==
+// GPUCompute.h:53-58): x mod 32, bumped by one when it repeats this kangaroo's previous jump (2-cycle limiter).
+template <bool SYM>
+__device__ __forceinline__ u32 jump_index(u32 x0, u32 lastJump) {
+  const u32 j0 = x0 & 31u;
+  if (!SYM) return j0;
+  return (j0 == lastJump) ? ((lastJump + 1u) & 31u) : j0;
+}
+
 
 // Warp 0 only: turn the T per-thread products in sTot into their T inverses (in place).
 // lane l chains the totals of threads {l, l+32, ...} (one per warp: conflict-free), the 32 lane products are
@@ -111,11 +123,12 @@ __device__ __noinline__ void tile_inverse(uint4* sTot, int lane, unsigned long l
   sts_fe(sTot, lane, T + lane, inv);
 }
 
-template <int T, int K>
+template <int T, int K, bool SYM>
 __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchParams p) {
   using C = Cfg<T, K>;
   constexpr int TILE = C::TILE;
   extern __shared__ uint4 smem[];
+  uint8_t* sL = reinterpret_cast<uint8_t*>(smem) + C::LJ_OFF;
   uint4* sX = smem + C::S_X;
   uint4* sY = smem + C::S_Y;
   uint4* sP = smem + C::S_P;
@@ -141,6 +154,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
       sY[(g * 2 + 0) * T + t] = gsrc[(g * CHUNKS + 2) * T + t];
       sY[(g * 2 + 1) * T + t] = gsrc[(g * CHUNKS + 3) * T + t];
       sD[g * T + t] = gsrc[(g * CHUNKS + 4) * T + t];
+      if (SYM) sL[g * T + t] = p.aux[(size_t)tile * TILE + g * T + t];
     }
     // prologue: forward chain of dx = x - jPx[x & 31]; sP[g] = product of the dx before g
     u32 P[8];
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
 #pragma unroll 1
       for (int g = 0; g < K; g++) {
         lds_fe(x, sX, (g * 2) * T + t, (g * 2 + 1) * T + t);
-        lds_jp(jx, jpx, x[0] & 31u);
+        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u));
         fe_sub(dx, x, jx);
         if (g == 0) {
           u32 one[8]; fe_set_one(one);
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
         u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8];
         lds_fe(x, sX, i0, i1);
         lds_fe(inv, sP, i0, i1);                 // prefix of this kangaroo
-        const u32 j = x[0] & 31u;
+        const u32 j = jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u);
         lds_jp(jx, jpx, j);
         fe_sub(dx, x, jx);
         fe_mul(inv, inv, I);                     // 1/dx
@@ -199,11 +213,17 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
         fe_sub(ry, x, rx);
         fe_mul(ry, ry, s);
         fe_sub(ry, ry, y);                       // ry = s (x - rx) - y
-        sts_fe(sX, i0, i1, rx);
-        sts_fe(sY, i0, i1, ry);
         uint4 dv = sD[g * T + t];
         u32 d[4] = {dv.x, dv.y, dv.z, dv.w};
         d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+        if (SYM) {                               // class switch (Check.cpp:551-556), see stream_body
+          const u32 neg = fe_gt_half_mask(ry);
+          fe_cneg(ry, neg);
+          d128_cneg(d, neg);
+          sL[g * T + t] = (uint8_t)j;
+        }
+        sts_fe(sX, i0, i1, rx);
+        sts_fe(sY, i0, i1, ry);
         sD[g * T + t] = make_uint4(d[0], d[1], d[2], d[3]);
         if (((rx[7] & mhi) | (rx[6] & mlo)) == 0u) {          // GPUCompute.h:96
           const u64 kidx = (u64)tile * TILE + (u64)g * T + (u64)t;
@@ -219,7 +239,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
           }
         }
         if (!last) {                             // next jump's dx and prefix, accumulated in THIS order
-          lds_jp(jx, jpx, rx[0] & 31u);
+          lds_jp(jx, jpx, jump_index<SYM>(rx[0], j));
           fe_sub(dx, rx, jx);
           if (i == 0) {
             u32 one[8]; fe_set_one(one);
@@ -243,6 +263,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
       gdst[(g * CHUNKS + 2) * T + t] = sY[(g * 2 + 0) * T + t];
       gdst[(g * CHUNKS + 3) * T + t] = sY[(g * 2 + 1) * T + t];
       gdst[(g * CHUNKS + 4) * T + t] = sD[g * T + t];
+      if (SYM) p.aux[(size_t)tile * TILE + g * T + t] = sL[g * T + t];
     }
   }
 }
@@ -256,16 +277,17 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
 // next kangaroo while the current one is in the multiplier.  HBM traffic 224 B/jump instead of 2.5, but no
 // serial section at all; selected with KGX_MODE=stream (see DESIGN.md for the measured trade-off).
 // =====================================================================================================
-struct KangLoad { uint4 p0, p1, x0, x1, y0, y1, d; };
+struct KangLoad { uint4 p0, p1, x0, x1, y0, y1, d; u32 lj; };
 
 // sg / pg point at this thread's column of kangaroo g: sg = st + g*CHUNKS*T, pg = pr + g*2*T (running pointers: the
 // hot loop does no index multiplications -- IMAD shares the binding pipe)
-template <int T>
-__device__ __forceinline__ void stream_load(KangLoad& k, const uint4* sg, const uint4* pg) {
+template <int T, bool SYM>
+__device__ __forceinline__ void stream_load(KangLoad& k, const uint4* sg, const uint4* pg, const uint8_t* ag) {
   k.p0 = pg[0]; k.p1 = pg[T];
   k.x0 = sg[0]; k.x1 = sg[T];
   k.y0 = sg[2 * T]; k.y1 = sg[3 * T];
   k.d = sg[4 * T];
+  if (SYM) k.lj = ag[0];
 }
 __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) {
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
@@ -289,13 +311,13 @@ __device__ __noinline__ void emit_dp_from_state(const LaunchParams& p, const uin
 
 // One kangaroo of the fused pass (see the file header): back-substitute, jump, start the next chain.  Branch-free:
 // returns whether the new point is distinguished (x' and d' are in the state chunks for emit_dp_from_state).
-template <int T>
-__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, const u32* jpx, const u32* jpy,
+template <int T, bool SYM>
+__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, uint8_t* ag, const u32* jpx, const u32* jpy,
                                             const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi) {
   u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8], d[4];
   unpack8(x, cur.x0, cur.x1);
   unpack8(inv, cur.p0, cur.p1);
-  const u32 j = x[0] & 31u;
+  const u32 j = jump_index<SYM>(x[0], cur.lj);
   lds_jp(jx, jpx, j);
   fe_sub(dx, x, jx);
   fe_mul(inv, inv, I);                     // 1/dx
@@ -310,15 +332,21 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
   fe_sub(ry, x, rx);
   fe_mul(ry, ry, s);
   fe_sub(ry, ry, y);                       // ry = s (x - rx) - y
+  d[0] = cur.d.x; d[1] = cur.d.y; d[2] = cur.d.z; d[3] = cur.d.w;
+  d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+  if (SYM) {                               // equivalence class switch (Check.cpp:551-556): y > (p-1)/2 -> (x, p - y), d -> -d
+    const u32 neg = fe_gt_half_mask(ry);
+    fe_cneg(ry, neg);
+    d128_cneg(d, neg);                     // signed 128-bit distance
+    ag[0] = (uint8_t)j;                    // lastJump
+  }
   sg[0] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
   sg[T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
   sg[2 * T] = make_uint4(ry[0], ry[1], ry[2], ry[3]);
   sg[3 * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
-  d[0] = cur.d.x; d[1] = cur.d.y; d[2] = cur.d.z; d[3] = cur.d.w;
-  d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
   sg[4 * T] = make_uint4(d[0], d[1], d[2], d[3]);
   // next jump's dx and prefix product, accumulated in THIS order (P starts at 1 for the first kangaroo of a pass)
-  lds_jp(jx, jpx, rx[0] & 31u);
+  lds_jp(jx, jpx, jump_index<SYM>(rx[0], j));
   fe_sub(dx, rx, jx);
   pg[0] = make_uint4(P[0], P[1], P[2], P[3]);
   pg[T] = make_uint4(P[4], P[5], P[6], P[7]);
@@ -347,7 +375,7 @@ __device__ __forceinline__ void stream_group_inverse(u32* I, const u32* P) {
   for (int l = 4; l >= 0; l--) fe_mul(I, I, sib[l]);       // -> 1 / (this lane's own product)
 }
 
-template <int T, int CTAS, bool WARPINV>
+template <int T, int CTAS, bool WARPINV, bool SYM>
 __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
   const int G = p.G;     // even: the fused pass is unrolled by two
   __shared__ u32 sJ[JT_WORDS];
@@ -363,6 +391,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
     uint4* st = p.state + (size_t)tile * (G * CHUNKS * T) + t;
     uint4* pr = p.pre + (size_t)tile * (G * 2 * T) + t;
     const u64 kbase = (u64)tile * (T * G) + (u64)t;
+    uint8_t* au = SYM ? (p.aux + (size_t)tile * ((size_t)G * T) + t) : nullptr;
     u32 P[8];
     fe_set_one(P);
     {   // prologue: forward chain, pr[g] = product of the dx before g
@@ -370,7 +399,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
 #pragma unroll 1
       for (int g = 0; g < G; g++) {
         unpack8(x, st[(g * CHUNKS + 0) * T], st[(g * CHUNKS + 1) * T]);
-        lds_jp(jx, jpx, x[0] & 31u);
+        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)au[(size_t)g * T] : 0u));
         fe_sub(dx, x, jx);
         pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
         fe_mul(P, P, dx);
@@ -387,18 +416,20 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
       const long long dk = backward ? -(long long)T : (long long)T;
       uint4* sg = st + (size_t)g0 * (CHUNKS * T);
       uint4* pg = pr + (size_t)g0 * (2 * T);
+      uint8_t* ag = SYM ? (au + (size_t)g0 * T) : nullptr;
       u64 kidx = kbase + (u64)g0 * T;
       KangLoad A, B;                              // ping-pong prefetch buffers (no register copies)
-      stream_load<T>(A, sg, pg);
+      stream_load<T, SYM>(A, sg, pg, ag);
 #pragma unroll 1
       for (int i = 0; i < G; i += 2) {
-        stream_load<T>(B, sg + ds, pg + dp);
-        const bool ha = stream_body<T>(A, sg, pg, jpx, jpy, jd, I, P, mlo, mhi);
-        if (i + 2 < G) stream_load<T>(A, sg + 2 * ds, pg + 2 * dp);
-        const bool hb = stream_body<T>(B, sg + ds, pg + dp, jpx, jpy, jd, I, P, mlo, mhi);
+        stream_load<T, SYM>(B, sg + ds, pg + dp, ag + dk);
+        const bool ha = stream_body<T, SYM>(A, sg, pg, ag, jpx, jpy, jd, I, P, mlo, mhi);
+        if (i + 2 < G) stream_load<T, SYM>(A, sg + 2 * ds, pg + 2 * dp, ag + 2 * dk);
+        const bool hb = stream_body<T, SYM>(B, sg + ds, pg + dp, ag + dk, jpx, jpy, jd, I, P, mlo, mhi);
         if (ha) emit_dp_from_state<T>(p, sg, kidx);
         if (hb) emit_dp_from_state<T>(p, sg + ds, kidx + dk);
         sg += 2 * ds; pg += 2 * dp; kidx += 2 * dk;
+        if (SYM) ag += 2 * dk;
       }
       backward ^= 1;
     }
@@ -408,7 +439,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
 // ---- host AoS (kIdx order) <-> tile layout --------------------------------------------------------------
 // slot s -> tile = s / TILE, g = (s % TILE) / T, t = s % T.  Padding slots (s >= n) replicate kangaroo s % n
 // so that every tile is full of valid walkers; their DPs are dropped by the kidx < nKangaroos test.
-__global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, const uint4* d, u64 n, u64 nPadded, int T, int K) {
+__global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, const uint4* d, u64 n, u64 nPadded, int T, int K, uint8_t* aux) {
   const int TILE = T * K;
   u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nPadded) return;
@@ -420,6 +451,7 @@ __global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, cons
   dst[(g * CHUNKS + 2) * T + t] = py[2 * src];
   dst[(g * CHUNKS + 3) * T + t] = py[2 * src + 1];
   dst[(g * CHUNKS + 4) * T + t] = d[src];
+  if (aux) aux[tile * TILE + (u64)g * T + t] = 32;     // lastJump = NB_JUMP: none yet (GPUEngine.cu:413-416)
 }
 __global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d, u64 n, int T, int K) {
   const int TILE = T * K;
@@ -434,11 +466,12 @@ __global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d
   d[s] = src[(g * CHUNKS + 4) * T + t];
 }
 struct PatchArgs { uint4 c[CHUNKS]; };
-__global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K) {
+__global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K, uint8_t* aux) {
   const int TILE = T * K;
   u64 tile = s / TILE; int r = (int)(s % TILE); int g = r / T, t = r % T;
   uint4* dst = state + tile * (K * CHUNKS * T);
   if (threadIdx.x < CHUNKS) dst[(g * CHUNKS + threadIdx.x) * T + t] = a.c[threadIdx.x];
+  if (aux && threadIdx.x == 0) aux[tile * TILE + (u64)g * T + t] = 32;   // GPUEngine.cu:532-536
 }
 
 // ---- device-side HashTable::Convert (HashTable.cpp:75-100) -------------------------------------------
@@ -446,7 +479,8 @@ __global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K) {
 // DP {u32 kIdx; u32 h; int128 x; int128 d} (Kangaroo.h:94-101): h = x.bits64[2] & 0x3FFFF, x = 128 LSBs,
 // d = |distance| (126 bits) | sign << 127 | type << 126 with distance = biased d - wildOffset for wild kangaroos
 // (GPUEngine.cu:672) taken as a signed value (the reference forms it mod n and tests the top bit).
-__global__ void dp_convert_kernel(const u32* __restrict__ slab, u32* __restrict__ out40, u32 maxFound, u64 wo0, u64 wo1) {
+// signedMode (symmetric engine): the record's distance is a signed 128-bit two's complement value, no wild offset.
+__global__ void dp_convert_kernel(const u32* __restrict__ slab, u32* __restrict__ out40, u32 maxFound, u64 wo0, u64 wo1, int signedMode) {
   const u32 cnt = min(slab[0], maxFound);
   if (blockIdx.x == 0 && threadIdx.x == 0) out40[0] = cnt;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
@@ -456,7 +490,9 @@ __global__ void dp_convert_kernel(const u32* __restrict__ slab, u32* __restrict_
     const u32 type = (u32)(kidx & 1ull);
     u64 d0 = (u64)r[8] | ((u64)r[9] << 32), d1 = (u64)r[10] | ((u64)r[11] << 32);
     u64 sign = 0;
-    if (type) {                                   // wild: subtract the offset, keep magnitude + sign
+    if (signedMode) {
+      if (d1 >> 63) { d0 = ~d0 + 1; d1 = ~d1 + (d0 == 0); sign = 1ull << 63; }
+    } else if (type) {                            // wild: subtract the offset, keep magnitude + sign
       const u64 b0 = d0 < wo0;
       u64 t0 = d0 - wo0, t1 = d1 - wo1 - b0;
       const bool neg = (d1 < wo1) || (d1 == wo1 && d0 < wo0);

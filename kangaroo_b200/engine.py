@@ -134,8 +134,17 @@ class GPUEngine:
         self.dpMask = dpMask
         self._ck(self._lib.kgx_set_params(self._h, ctypes.c_uint64(dpMask), _p(jd), _p(jx), _p(jy)), "SetParams")
 
+    def SetSymmetry(self, on=True):
+        """USE_SYMMETRY engine mode (reference: compile-time Constants.h:25): lastJump limiter + equivalence-class switch on
+        the device; distances cross the ABI as signed 128-bit values, the wild offset is not applied.  Before SetKangaroos."""
+        self._ck(self._lib.kgx_set_symmetry(self._h, int(bool(on))), "SetSymmetry")
+        self.symmetry = bool(on)
+
     def _bias(self, d, kidx0=0):
-        """+wildOffset mod n on odd kIdx (GPUEngine.cu:407-411), then truncate to 128 bits like the reference."""
+        """+wildOffset mod n on odd kIdx (GPUEngine.cu:407-411), then truncate to 128 bits like the reference.
+        Symmetric mode: d mod n -> signed 128-bit two's complement (values above n/2 are negative), no offset."""
+        if getattr(self, "symmetry", False):
+            return [((v - ORDER) if v > ORDER // 2 else v) & ((1 << 128) - 1) for v in d]
         out = []
         for i, v in enumerate(d):
             if (kidx0 + i) % 2 == WILD:
@@ -144,6 +153,8 @@ class GPUEngine:
         return out
 
     def _unbias(self, v, kidx):
+        if getattr(self, "symmetry", False):                          # signed 128-bit -> mod n
+            return (v - (1 << 128)) % ORDER if v >> 127 else v
         return (v - self.wildOffset) % ORDER if kidx % 2 == WILD else v
 
     def SetKangaroos(self, px, py, d):

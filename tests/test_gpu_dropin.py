@@ -60,13 +60,13 @@ def test_checkpoint_round_trip_through_reference_work_files(tmp_path):
     GPUEngine::GetKangaroos (Kangaroo.cpp:618-626) and Backup.cpp:449-572 writes HEADW + hash table + every kangaroo; `-i f`
     reads it back (Backup.cpp:291-364) and the search goes on from the saved herd through SetKangaroos.  Everything but the
     engine is the reference's own code, so passing means the engine's Get/SetKangaroos round trip is exact at full size
-    (4.85 M kangaroos, 466 MB of walks).  Run 1 saves at the first status tick (2 s) and gives up at 25 % of the expected
-    operations (-m); `-wcheck` validates every stored DP (d*G [+P] == x); run 2 resumes from the file and must find the key."""
+    (4.85 M kangaroos, 466 MB of walks).  Run 1 saves at every status tick (`-wi 1`: Timer::get_tick() counts from program
+    start, Thread.cpp:330-335) and gives up at 25 % of the expected operations (-m); `-wcheck` validates every stored DP (d*G [+P] == x); run 2 resumes from the file and must find the key."""
     work = str(tmp_path / "k.work")
     cfg = os.path.join(GOLD, "puzzle110_window72.txt")
     out1 = ""
     for attempt in range(3):                                          # a lucky run may solve before the first save
-        out1 = run(["-t", "0", "-gpu", "-d", "14", "-w", work, "-wi", "1000", "-ws", "-m", "0.25", cfg], timeout=600)
+        out1 = run(["-t", "0", "-gpu", "-d", "14", "-w", work, "-wi", "1", "-ws", "-m", "0.25", cfg], timeout=600)
         if os.path.exists(work) and "Aborted" in out1:
             break
     assert os.path.exists(work) and "SaveWork" in out1 and "Aborted" in out1, out1[-2000:]

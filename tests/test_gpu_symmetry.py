@@ -1,0 +1,147 @@
+"""-m gpu: USE_SYMMETRY engine mode.
+
+Parity definition = the symmetric walk the reference's own `Kangaroo::Check` replays on the CPU when it is compiled with
+USE_SYMMETRY (Check.cpp:534-556): jump = x mod 32 bumped when it repeats the kangaroo's previous jump, P += J, d += jD mod n,
+class switch (y > (p-1)/2 -> y = p - y, d = n - d).  Restated in oracle/kgx_oracle.c (kgo_jump_sym), pinned to the reference's
+Int code by tests/test_oracle_vs_ref.py.  Checked here
+  * through the C ABI on every jump kernel (state + DP multiset, several launches so lastJump persists across launches),
+  * through the reference's UNMODIFIED host compiled with -DUSE_SYMMETRY and linked to the engine (build/kangaroo_b200_sym):
+    its own `-check` prints CPU/GPU ok -- which the reference's own symmetric GPU kernel cannot (symmetry),
+  * statistically: operations per solved key with and without symmetry (the reference's -DSTATS counters), ~1/sqrt(2)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from kangaroo_b200 import GPUEngine, NB_RUN
+from oracle import kgo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def sym_case(oracle, n, rp=64, seed=1, first_type=0):
+    table = oracle.create_jump_table_sym(rp)
+    key = oracle.ec_mul_g(0x5B3F38AF935A3640D158E871CE6E9666DB862636383386EE0000000000123000)
+    wdiv4 = ((1 << rp) - 1) >> 2
+    oracle.rseed(seed)
+    px, py, d = oracle.create_herd_sym(n, rp, wdiv4, key, first_type)
+    return dict(table=table, key=key, px=px, py=py, d=d, n=n, rp=rp)
+
+
+@pytest.mark.parametrize("grid", [(2, 4), (3, 5), (16, 8)])
+def test_symmetric_walk_matches_oracle(oracle, kernel, grid):
+    n = grid[0] * grid[1] * 128
+    case = sym_case(oracle, n, seed=grid[0] * 10 + grid[1])
+    eng = GPUEngine(grid[0], grid[1], 0, 1 << 17, **kernel)
+    eng.SetSymmetry(True)
+    mask = oracle.dp_mask(7)
+    eng.SetParams(mask, *case["table"])
+    eng.SetWildOffset(((1 << 64) - 1) >> 2)            # what the host passes (Kangaroo.cpp:548-550); not applied in this mode
+    eng.SetKangaroos(case["px"], case["py"], kgo.array_to_ints(case["d"]))
+    px, py, d = case["px"].copy(), case["py"].copy(), case["d"].copy()
+    lj = np.full(n, 32, dtype=np.uint8)
+    eng.callKernel()
+    for launch in range(3):                            # lastJump must survive between launches
+        found = eng.Launch()
+        want = oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, grp=256, max_dp=1 << 20)
+        assert sorted((it.x, it.d, it.kIdx) for it in found) == sorted((x, dd, k) for x, dd, k, j in want), launch
+        assert len(found) > 0
+    want = oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, grp=256, max_dp=1 << 20)     # launch 4 is in flight
+    gx, gy, gd = eng.GetKangaroos()
+    assert gx == kgo.array_to_ints(px) and gy == kgo.array_to_ints(py) and gd == kgo.array_to_ints(d)
+    half = (kgo.P - 1) // 2
+    assert max(gy) <= half                             # every point is its class representative
+    assert any(v > kgo.N // 2 for v in gd)             # negative distances were exercised
+    eng.sync(); eng.close()
+
+
+def test_symmetric_set_kangaroo_resets_last_jump(oracle, kernel):
+    """SetKangaroo stores lastJump = NB_JUMP for the patched kangaroo (GPUEngine.cu:532-536)."""
+    n = 2 * 2 * 128
+    case = sym_case(oracle, n, seed=5)
+    eng = GPUEngine(2, 2, 0, 1 << 16, **kernel)
+    eng.SetSymmetry(True)
+    mask = oracle.dp_mask(16)
+    eng.SetParams(mask, *case["table"])
+    eng.SetKangaroos(case["px"], case["py"], kgo.array_to_ints(case["d"]))
+    px, py, d = case["px"].copy(), case["py"].copy(), case["d"].copy()
+    lj = np.full(n, 32, dtype=np.uint8)
+    eng.callKernel(); eng.Launch(relaunch=False)
+    oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask)
+    r = 77
+    oracle.rseed(31337)
+    nx, ny, nd = oracle.create_herd_sym(1, 64, ((1 << 64) - 1) >> 2, case["key"], r % 2)
+    px[r], py[r], d[r], lj[r] = nx[0], ny[0], nd[0], 32
+    eng.SetKangaroo(r, kgo.from_limbs(nx[0]), kgo.from_limbs(ny[0]), kgo.from_limbs(nd[0]))
+    eng.callKernel(); eng.Launch(relaunch=False)
+    oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask)
+    gx, gy, gd = eng.GetKangaroos()
+    assert gx == kgo.array_to_ints(px) and gy == kgo.array_to_ints(py) and gd == kgo.array_to_ints(d)
+    eng.close()
+
+
+def test_symmetric_device_herd_matches_reference_formula(oracle, kernel):
+    """kgx_create_herd in symmetric mode == Kangaroo::CreateHerd's USE_SYMMETRY branch (Kangaroo.cpp:686-734)."""
+    n = 2 * 128
+    case = sym_case(oracle, n, seed=9)
+    # the oracle's d already carries the class switch; recover the drawn distances by undoing it where y was flipped
+    key = case["key"]
+    raw = []
+    for i in range(n):
+        dv = kgo.from_limbs(case["d"][i])
+        pt = oracle.ec_mul_g(dv) if i % 2 == 0 else oracle.ec_add(key, oracle.ec_mul_g(dv))
+        raw.append(dv if pt[1] == kgo.from_limbs(case["py"][i]) else (kgo.N - dv) % kgo.N)
+    eng = GPUEngine(2, 1, 0, 65536, **kernel)
+    eng.SetSymmetry(True)
+    eng.CreateHerd(raw, key)
+    gx, gy, gd = eng.GetKangaroos()
+    assert gx == kgo.array_to_ints(case["px"]) and gy == kgo.array_to_ints(case["py"]) and gd == kgo.array_to_ints(case["d"])
+    eng.close()
+
+
+def run(binary, args, timeout=900, env=None, cwd=None):
+    exe = os.path.join(ROOT, "build", binary)
+    if not os.path.exists(exe):
+        pytest.skip("build/%s not built (needs the reference sources at build time)" % binary)
+    e = dict(os.environ); e.update(env or {})
+    p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout, cwd=cwd or ROOT, env=e)
+    return (p.stdout + p.stderr).replace("\r", "\n")
+
+
+@pytest.mark.parametrize("env", [{"KGX_MODE": "stream", "KGX_STREAM_G": "128"}, {"KGX_MODE": "resident"}], ids=["stream128", "resident"])
+def test_reference_check_with_use_symmetry(env):
+    """The reference host compiled with its own USE_SYMMETRY switch, its own Check.cpp:467-621 replay, our engine."""
+    out = run("kangaroo_b200_sym", ["-gpu", "-check", "-g", "8,128"], env=env)
+    assert "CPU/GPU ok" in out, out[-3000:]
+    assert "DP Mismatch" not in out and "not ok" not in out
+
+
+def test_symmetric_build_solves_in64():
+    out = run("kangaroo_b200_sym", ["-t", "0", "-gpu", "-g", "64,128", os.path.join(GOLD, "in64.txt")])
+    assert "5B3F38AF935A3640D158E871CE6E9666DB862636383386EE510F18CCC3BD72EB" in out.upper(), out[-2000:]
+
+
+def test_symmetry_gain_in_operations_per_key(tmp_path):
+    """64 keys in a 2^56 range, the reference's -DSTATS counters: average group operations per solved key in units of sqrt(N),
+    without and with symmetry.  Theory 2.08 vs 1.47 (ComputeExpected, Kangaroo.cpp:836-873); the ratio must be clearly < 1."""
+    cfg = os.path.join(GOLD, "in56_64keys.txt")
+    avgs = {}
+    for binary in ("kangaroo_b200_stats", "kangaroo_b200_sym_stats"):
+        out = run(binary, ["-t", "0", "-gpu", "-g", "8,128", "-d", "4", cfg], timeout=1500, cwd=str(tmp_path))
+        rows = re.findall(r"^\[\s*(\d+)\] 2\^([0-9.]+) Dead:(\d+) Avg:2\^([0-9.]+) DeadAvg:[0-9.]+ \(([0-9.]+) ([0-9.]+) sqrt\(N\)\)", out, re.M)
+        assert len(rows) == 64, out[-2000:]
+        assert out.count("Priv: 0x") == 64
+        avgs[binary] = (float(rows[-1][4]), float(rows[-1][5]))
+        print("%s: avg %.3f sqrt(N) per key (expected %.3f)" % (binary, *avgs[binary]))
+    plain, sym = avgs["kangaroo_b200_stats"][0], avgs["kangaroo_b200_sym_stats"][0]
+    assert sym < 0.88 * plain, avgs
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "symmetry_gain.txt"), "w") as f:
+        f.write("64 keys, 2^56 range, grid 8x128, dp 4, reference host (-DSTATS) + B200 engine\n")
+        f.write("plain    : %.3f sqrt(N) operations per key (reference's estimate %.3f)\n" % avgs["kangaroo_b200_stats"])
+        f.write("symmetry : %.3f sqrt(N) operations per key (reference's estimate %.3f)\n" % avgs["kangaroo_b200_sym_stats"])
+        f.write("ratio    : %.3f (theory 0.707)\n" % (sym / plain))
