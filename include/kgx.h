@@ -61,13 +61,19 @@ const char* kgx_last_error(kgx_engine* e);      /* e may be NULL: error of the l
 uint64_t    kgx_num_kangaroos(kgx_engine* e);   /* groups * threads_per_group * 128 */
 uint64_t    kgx_memory_bytes(kgx_engine* e);    /* device bytes held (GPUEngine::GetMemory) */
 
-/* --- USE_SYMMETRY engine mode (reference: compile-time switch Constants.h:25; device side GPUCompute.h:27-60, 91-94,
- *     GPUMath.h:518-547; parity definition Check.cpp:534-556).  on != 0: every jump uses the lastJump 2-cycle limiter and the
- *     equivalence-class switch (y > (p-1)/2 -> point negated, distance negated).  Distances crossing this ABI (upload,
- *     download, patch, create_herd, DP items) are then SIGNED 128-bit two's complement values and NO wild offset is applied
- *     (the reference's biased-unsigned device form cannot represent the sign changes: its ModNeg256Order writes 256 bits
- *     into a 128-bit slot).  lastJump is reset to "none" by upload / patch / create_herd like GPUEngine.cu:413-416, 532-536.
- *     Call before the herd is uploaded. --- */
+/* --- USE_SYMMETRY engine mode (reference: compile-time switch Constants.h:25).  mode:
+ *       0                    off
+ *       KGX_SYM_LASTJUMP (1) the reference's DEVICE rule (GPUCompute.h:53-60, 91-94), which Kangaroo::Check replays on the CPU
+ *                            (Check.cpp:534-556): jump = x mod 32, bumped when it repeats the previous jump of the kangaroo
+ *       KGX_SYM_CLASS    (2) the rule of the reference's working symmetric path SolveKeyCPU (Kangaroo.cpp:381-384, 422-428):
+ *                            jump = x mod 16 + 16 * symClass, symClass flipping at every class switch
+ *     Both apply the equivalence-class switch after every jump (y > (p-1)/2 -> point negated, distance negated).  Distances
+ *     crossing this ABI (upload, download, patch, create_herd, DP items) are then SIGNED 128-bit two's complement values and
+ *     NO wild offset is applied (the reference's biased-unsigned device form cannot represent the sign changes: its
+ *     ModNeg256Order writes 256 bits into a 128-bit slot, GPUMath.h:533-547).  The per-kangaroo rule state (lastJump /
+ *     symClass) is reset by upload / patch / create_herd like GPUEngine.cu:413-416, 532-536.  Call before the herd is uploaded. --- */
+#define KGX_SYM_LASTJUMP 1
+#define KGX_SYM_CLASS    2
 int kgx_set_symmetry(kgx_engine* e, int on);
 int kgx_get_symmetry(kgx_engine* e);
 

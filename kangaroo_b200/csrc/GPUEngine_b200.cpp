@@ -9,6 +9,7 @@
 // and run unmodified:  see kangaroo_b200/csrc/build_dropin.sh and INTEGRATION.md.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "GPU/GPUEngine.h"
@@ -69,7 +70,14 @@ GPUEngine::GPUEngine(int nbThreadGroup, int nbThreadPerGroup, int gpuId, uint32_
   if (!e) { printf("GPUEngine: %s\n", kgx_last_error(NULL)); return; }        // callers never check (Kangaroo.cpp:523-526)
   inputKangaroo = reinterpret_cast<uint64_t*>(e);
 #ifdef USE_SYMMETRY
-  if (kgx_set_symmetry(e, 1) != 0) { printf("GPUEngine: %s\n", kgx_last_error(e)); kgx_destroy(e); inputKangaroo = NULL; return; }
+  // Which of the reference's two symmetric jump rules the engine runs (include/kgx.h): the one its working path uses
+  // (SolveKeyCPU: symClass) unless KGX_SYM_RULE=lastjump asks for the device/Check.cpp rule -- `-check` needs the latter.
+  int symRule = KGX_SYM_CLASS;
+  if (const char* r = getenv("KGX_SYM_RULE")) {
+    if (!strcmp(r, "lastjump")) symRule = KGX_SYM_LASTJUMP;
+    else if (strcmp(r, "symclass")) printf("GPUEngine: KGX_SYM_RULE must be lastjump or symclass (using symclass)\n");
+  }
+  if (kgx_set_symmetry(e, symRule) != 0) { printf("GPUEngine: %s\n", kgx_last_error(e)); kgx_destroy(e); inputKangaroo = NULL; return; }
 #endif
   outputItemPinned = reinterpret_cast<uint32_t*>(new kgx_item[maxFound]);
   kangarooSize = (uint32_t)kgx_memory_bytes(e);

@@ -28,7 +28,9 @@ struct kgx_engine {
   uint4* pre = nullptr;      // streaming mode: prefix-product scratch
   bool streamMode = false;
   int streamCtas = 2;
-  bool symmetry = false;     // USE_SYMMETRY engine mode (kgx_set_symmetry): lastJump limiter + class switch, signed distances
+  bool symmetry = false;     // USE_SYMMETRY engine mode (kgx_set_symmetry): class switch + cycle rule, signed distances
+  int symRule = 0;           // KGX_SYM_LASTJUMP / KGX_SYM_CLASS
+  int pfDist = 0;            // KGX_STREAM_PF: L2 prefetch distance of the stream kernel (kangaroos)
   uint8_t* aux = nullptr;    // symmetric mode: lastJump per slot
   bool warpInv = true;       // stream kernel: one warp-wide shuffle-butterfly inverse per pass (false: one per thread)
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]
@@ -196,6 +198,7 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
       // thread for short ones, where the butterfly's 10 extra multiplications per lane weigh more than lane divergence inside
       // the variable-time inverse -- measured equal at G = 128 (14.16 vs 14.23 GJump/s), 3 % apart at G = 28 (profiles/r2b_sweep.txt)
       if (!invChosen) e->warpInv = g >= 64;
+      if (const char* pf = getenv("KGX_STREAM_PF")) e->pfDist = atoi(pf);
       e->streamCtas = ctas;
       e->T = 128; e->K = (int)g; e->smemBytes = 0; e->ctasPerSM = ctas;
     }
@@ -262,16 +265,16 @@ int kgx_set_symmetry(kgx_engine* e, int on) {
   if (on && e->streamMode && e->streamCtas != 2) {
     snprintf(e->err, sizeof e->err, "kgx_set_symmetry: the symmetric stream kernel is the 2-CTA variant only"); return -1;
   }
-  if (on && !e->aux) {
-    CK(e, cudaMalloc(&e->aux, e->nPadded));
-    CK(e, cudaMemsetAsync(e->aux, 32, e->nPadded, e->stream));
-  }
+  if (on != 0 && on != KGX_SYM_LASTJUMP && on != KGX_SYM_CLASS) { snprintf(e->err, sizeof e->err, "kgx_set_symmetry: mode must be 0, 1 (lastJump rule) or 2 (symClass rule)"); return -1; }
+  if (on && !e->aux) CK(e, cudaMalloc(&e->aux, e->nPadded));
+  if (on) CK(e, cudaMemsetAsync(e->aux, on == KGX_SYM_CLASS ? 0 : 32, e->nPadded, e->stream));
+  e->symRule = on;
   if (on && !e->streamMode)
     CK(e, cudaFuncSetAttribute(g_cfgs[e->cfg].kernSym, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smemBytes));
   e->symmetry = on != 0;
   return 0;
 }
-int kgx_get_symmetry(kgx_engine* e) { return e->symmetry ? 1 : 0; }
+int kgx_get_symmetry(kgx_engine* e) { return e->symmetry ? e->symRule : 0; }
 
 int kgx_set_params(kgx_engine* e, uint64_t dp_mask, const uint64_t* jd, const uint64_t* jpx, const uint64_t* jpy) {
   CK(e, cudaSetDevice(e->dev));
@@ -310,7 +313,7 @@ int kgx_upload(kgx_engine* e, const uint64_t* px, const uint64_t* py, const uint
   CK(e, cudaMemcpyAsync(e->stgY, py, e->n * 32, cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaMemcpyAsync(e->stgD, d, e->n * 16, cudaMemcpyHostToDevice, e->stream));
   u32 blocks = (u32)((e->nPadded + 255) / 256);
-  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K, e->aux);
+  pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K, e->aux, e->symRule == KGX_SYM_CLASS ? 0 : 32);
   e->launches++;
   CK(e, cudaGetLastError());
   CK(e, cudaStreamSynchronize(e->stream));
@@ -370,7 +373,7 @@ int kgx_patch(kgx_engine* e, uint64_t kidx, const uint64_t px[4], const uint64_t
   if (kidx >= e->n) { snprintf(e->err, sizeof e->err, "kgx_patch: kidx out of range"); return -1; }
   PatchArgs a;
   memcpy(&a.c[0], px, 32); memcpy(&a.c[2], py, 32); memcpy(&a.c[4], d, 16);
-  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a, e->T, e->K, e->aux);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
+  patch_kernel<<<1, 32, 0, e->stream>>>(e->state, kidx, a, e->T, e->K, e->aux, e->symRule == KGX_SYM_CLASS ? 0 : 32);   // stream order == the reference's blocking memcpy order (Kangaroo.cpp:607)
   e->launches++;
   CK(e, cudaGetLastError());
   // padding slots replicate kangaroo (s % n): keep them walking their stale copy -- harmless, their DPs are dropped.
@@ -405,7 +408,7 @@ int kgx_create_herd(kgx_engine* e, const uint64_t* scalars, const uint64_t* d128
     e->launches++;
     CK(e, cudaGetLastError());
     u32 blocks = (u32)((e->nPadded + 255) / 256);
-    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K, e->aux);
+    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->state, e->stgX, e->stgY, e->stgD, e->n, e->nPadded, e->T, e->K, e->aux, e->symRule == KGX_SYM_CLASS ? 0 : 32);
     e->launches++;
     CK(e, cudaGetLastError());
     CK(e, cudaStreamSynchronize(e->stream));
@@ -424,7 +427,7 @@ int kgx_launch_async(kgx_engine* e) {
   int sidx = e->cur ^ 1;
   LaunchParams p;
   p.state = e->state; p.jtab = e->jtab; p.out = e->slab[sidx]; p.dpMask = e->dpMask; p.nKangaroos = e->n;
-  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre; p.G = e->K; p.aux = e->aux;
+  p.numTiles = e->numTiles; p.maxFound = e->maxFound; p.nRun = e->nRun; p.prof = e->prof; p.pre = e->pre; p.G = e->K; p.aux = e->aux; p.symRule = e->symRule; p.pfDist = e->pfDist;
   CK(e, cudaMemsetAsync(e->slab[sidx], 0, 4, e->stream));            // GPUEngine.cu:543
   CK(e, cudaEventRecord(e->evStart[sidx], e->stream));
   u32 grid = (u32)(e->ctasPerSM * e->sms);

@@ -54,7 +54,9 @@ struct LaunchParams {
   int nRun;
   uint4* pre;            // streaming kernel only: prefix-product scratch [numTiles][G][2][T]
   int G;                 // streaming kernel only: kangaroos per thread (even, chosen by the engine from the herd size)
-  uint8_t* aux;          // symmetric mode only: lastJump per kangaroo, [numTiles][G or K][T] bytes (32 = none yet)
+  uint8_t* aux;          // symmetric mode only: one state byte per kangaroo, [numTiles][G or K][T] (see jump_index)
+  int symRule;           // KGX_SYM_LASTJUMP / KGX_SYM_CLASS
+  int pfDist;            // stream kernel: L2 prefetch distance in kangaroos (0 = off; KGX_STREAM_PF)
   unsigned long long* prof;   // optional: [0]=sum serial cycles, [1]=sum modinv cycles, [2]=sum parallel cycles, [3]=tile-steps (warp 0 of every CTA)
 };
 
@@ -77,15 +79,31 @@ __device__ __forceinline__ void shfl_xor_fe(u32* r, const u32* a, int mask) {
 
 __device__ __forceinline__ void fe_inv(u32* r, const u32* a) { modinv256(r, a); }
 
-// USE_SYMMETRY jump selection as the reference's parity test defines it across the GPUEngine boundary (Check.cpp:536-541 ==
-// GPUCompute.h:53-58): x mod 32, bumped by one when it repeats this kangaroo's previous jump (2-cycle limiter).
+// USE_SYMMETRY jump selection.  The reference has TWO rules behind its compile-time switch, and the engine offers both
+// (LaunchParams::symRule, one state byte per kangaroo in LaunchParams::aux):
+//   KGX_SYM_LASTJUMP (1): the device rule (GPUCompute.h:53-58), which is also what Kangaroo::Check replays on the CPU
+//       (Check.cpp:536-541): x mod 32, bumped by one when it repeats this kangaroo's previous jump.  aux = last jump index
+//       (32 = none yet).  It only suppresses 2-cycles: on long walks kangaroos fall into longer fruitless cycles and stop
+//       producing new distinguished points -- measured: the USE_SYMMETRY build does not solve in64 with it.
+//   KGX_SYM_CLASS (2): the rule of the reference's working symmetric path, SolveKeyCPU (Kangaroo.cpp:381-384, 422-428):
+//       x mod 16 + 16 * symClass, where symClass flips at every class switch, so that the jump taken after a negation comes
+//       from the other half of the table (distances multiples of u, resp. v: Kangaroo.cpp:763-806).  aux = symClass.
+#ifndef KGX_SYM_LASTJUMP
+#define KGX_SYM_LASTJUMP 1
+#define KGX_SYM_CLASS    2
+#endif
 template <bool SYM>
-__device__ __forceinline__ u32 jump_index(u32 x0, u32 lastJump) {
+__device__ __forceinline__ u32 jump_index(u32 x0, u32 aux, int rule) {
+  if (!SYM) return x0 & 31u;
   const u32 j0 = x0 & 31u;
-  if (!SYM) return j0;
-  return (j0 == lastJump) ? ((lastJump + 1u) & 31u) : j0;
+  const u32 jl = (j0 == aux) ? ((aux + 1u) & 31u) : j0;
+  const u32 jc = (x0 & 15u) | ((aux & 1u) << 4);
+  return rule == KGX_SYM_CLASS ? jc : jl;
 }
-
+// state byte after a jump with index j that did (neg != 0) or did not switch class
+__device__ __forceinline__ u32 sym_next_aux(u32 aux, u32 j, u32 neg, int rule) {
+  return rule == KGX_SYM_CLASS ? ((aux ^ neg) & 1u) : j;
+}
 
 // Warp 0 only: turn the T per-thread products in sTot into their T inverses (in place).
 // lane l chains the totals of threads {l, l+32, ...} (one per warp: conflict-free), the 32 lane products are
@@ -163,7 +181,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
 #pragma unroll 1
       for (int g = 0; g < K; g++) {
         lds_fe(x, sX, (g * 2) * T + t, (g * 2 + 1) * T + t);
-        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u));
+        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u, p.symRule));
         fe_sub(dx, x, jx);
         if (g == 0) {
           u32 one[8]; fe_set_one(one);
@@ -198,7 +216,9 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
         u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8];
         lds_fe(x, sX, i0, i1);
         lds_fe(inv, sP, i0, i1);                 // prefix of this kangaroo
-        const u32 j = jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u);
+        const u32 aux0 = SYM ? (u32)sL[g * T + t] : 0u;
+        const u32 j = jump_index<SYM>(x[0], aux0, p.symRule);
+        u32 aux1 = 0;
         lds_jp(jx, jpx, j);
         fe_sub(dx, x, jx);
         fe_mul(inv, inv, I);                     // 1/dx
@@ -220,7 +240,8 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
           const u32 neg = fe_gt_half_mask(ry);
           fe_cneg(ry, neg);
           d128_cneg(d, neg);
-          sL[g * T + t] = (uint8_t)j;
+          aux1 = sym_next_aux(aux0, j, neg, p.symRule);
+          sL[g * T + t] = (uint8_t)aux1;
         }
         sts_fe(sX, i0, i1, rx);
         sts_fe(sY, i0, i1, ry);
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
           }
         }
         if (!last) {                             // next jump's dx and prefix, accumulated in THIS order
-          lds_jp(jx, jpx, jump_index<SYM>(rx[0], j));
+          lds_jp(jx, jpx, jump_index<SYM>(rx[0], aux1, p.symRule));
           fe_sub(dx, rx, jx);
           if (i == 0) {
             u32 one[8]; fe_set_one(one);
@@ -313,11 +334,12 @@ __device__ __noinline__ void emit_dp_from_state(const LaunchParams& p, const uin
 // returns whether the new point is distinguished (x' and d' are in the state chunks for emit_dp_from_state).
 template <int T, bool SYM>
 __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, uint8_t* ag, const u32* jpx, const u32* jpy,
-                                            const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi) {
+                                            const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi, const int rule) {
   u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8], d[4];
   unpack8(x, cur.x0, cur.x1);
   unpack8(inv, cur.p0, cur.p1);
-  const u32 j = jump_index<SYM>(x[0], cur.lj);
+  const u32 j = jump_index<SYM>(x[0], cur.lj, rule);
+  u32 auxn = 0;
   lds_jp(jx, jpx, j);
   fe_sub(dx, x, jx);
   fe_mul(inv, inv, I);                     // 1/dx
@@ -338,7 +360,8 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
     const u32 neg = fe_gt_half_mask(ry);
     fe_cneg(ry, neg);
     d128_cneg(d, neg);                     // signed 128-bit distance
-    ag[0] = (uint8_t)j;                    // lastJump
+    auxn = sym_next_aux(cur.lj, j, neg, rule);
+    ag[0] = (uint8_t)auxn;                 // lastJump / symClass
   }
   sg[0] = make_uint4(rx[0], rx[1], rx[2], rx[3]);
   sg[T] = make_uint4(rx[4], rx[5], rx[6], rx[7]);
@@ -346,7 +369,7 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
   sg[3 * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
   sg[4 * T] = make_uint4(d[0], d[1], d[2], d[3]);
   // next jump's dx and prefix product, accumulated in THIS order (P starts at 1 for the first kangaroo of a pass)
-  lds_jp(jx, jpx, jump_index<SYM>(rx[0], j));
+  lds_jp(jx, jpx, jump_index<SYM>(rx[0], auxn, rule));
   fe_sub(dx, rx, jx);
   pg[0] = make_uint4(P[0], P[1], P[2], P[3]);
   pg[T] = make_uint4(P[4], P[5], P[6], P[7]);
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
 #pragma unroll 1
       for (int g = 0; g < G; g++) {
         unpack8(x, st[(g * CHUNKS + 0) * T], st[(g * CHUNKS + 1) * T]);
-        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)au[(size_t)g * T] : 0u));
+        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)au[(size_t)g * T] : 0u, p.symRule));
         fe_sub(dx, x, jx);
         pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
         fe_mul(P, P, dx);
@@ -422,10 +445,23 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
       stream_load<T, SYM>(A, sg, pg, ag);
 #pragma unroll 1
       for (int i = 0; i < G; i += 2) {
+        if (p.pfDist > 0 && i + p.pfDist + 1 < G) {      // pull the pair two trips ahead into L2 (no registers held)
+          const uint4* fs = sg + (ptrdiff_t)p.pfDist * ds;
+          const uint4* fp = pg + (ptrdiff_t)p.pfDist * dp;
+#pragma unroll
+          for (int c = 0; c < CHUNKS; c++) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fs + c * T));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fs + ds + c * T));
+          }
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + T));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + dp));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + dp + T));
+        }
         stream_load<T, SYM>(B, sg + ds, pg + dp, ag + dk);
-        const bool ha = stream_body<T, SYM>(A, sg, pg, ag, jpx, jpy, jd, I, P, mlo, mhi);
+        const bool ha = stream_body<T, SYM>(A, sg, pg, ag, jpx, jpy, jd, I, P, mlo, mhi, p.symRule);
         if (i + 2 < G) stream_load<T, SYM>(A, sg + 2 * ds, pg + 2 * dp, ag + 2 * dk);
-        const bool hb = stream_body<T, SYM>(B, sg + ds, pg + dp, ag + dk, jpx, jpy, jd, I, P, mlo, mhi);
+        const bool hb = stream_body<T, SYM>(B, sg + ds, pg + dp, ag + dk, jpx, jpy, jd, I, P, mlo, mhi, p.symRule);
         if (ha) emit_dp_from_state<T>(p, sg, kidx);
         if (hb) emit_dp_from_state<T>(p, sg + ds, kidx + dk);
         sg += 2 * ds; pg += 2 * dp; kidx += 2 * dk;
@@ -439,7 +475,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
 // ---- host AoS (kIdx order) <-> tile layout --------------------------------------------------------------
 // slot s -> tile = s / TILE, g = (s % TILE) / T, t = s % T.  Padding slots (s >= n) replicate kangaroo s % n
 // so that every tile is full of valid walkers; their DPs are dropped by the kidx < nKangaroos test.
-__global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, const uint4* d, u64 n, u64 nPadded, int T, int K, uint8_t* aux) {
+__global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, const uint4* d, u64 n, u64 nPadded, int T, int K, uint8_t* aux, int auxInit) {
   const int TILE = T * K;
   u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nPadded) return;
@@ -451,7 +487,7 @@ __global__ void pack_kernel(uint4* state, const uint4* px, const uint4* py, cons
   dst[(g * CHUNKS + 2) * T + t] = py[2 * src];
   dst[(g * CHUNKS + 3) * T + t] = py[2 * src + 1];
   dst[(g * CHUNKS + 4) * T + t] = d[src];
-  if (aux) aux[tile * TILE + (u64)g * T + t] = 32;     // lastJump = NB_JUMP: none yet (GPUEngine.cu:413-416)
+  if (aux) aux[tile * TILE + (u64)g * T + t] = (uint8_t)auxInit;   // lastJump = NB_JUMP: none yet (GPUEngine.cu:413-416) / symClass = 0 (Kangaroo.cpp:345-347)
 }
 __global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d, u64 n, int T, int K) {
   const int TILE = T * K;
@@ -466,12 +502,12 @@ __global__ void unpack_kernel(const uint4* state, uint4* px, uint4* py, uint4* d
   d[s] = src[(g * CHUNKS + 4) * T + t];
 }
 struct PatchArgs { uint4 c[CHUNKS]; };
-__global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K, uint8_t* aux) {
+__global__ void patch_kernel(uint4* state, u64 s, PatchArgs a, int T, int K, uint8_t* aux, int auxInit) {
   const int TILE = T * K;
   u64 tile = s / TILE; int r = (int)(s % TILE); int g = r / T, t = r % T;
   uint4* dst = state + tile * (K * CHUNKS * T);
   if (threadIdx.x < CHUNKS) dst[(g * CHUNKS + threadIdx.x) * T + t] = a.c[threadIdx.x];
-  if (aux && threadIdx.x == 0) aux[tile * TILE + (u64)g * T + t] = 32;   // GPUEngine.cu:532-536
+  if (aux && threadIdx.x == 0) aux[tile * TILE + (u64)g * T + t] = (uint8_t)auxInit;   // GPUEngine.cu:532-536
 }
 
 // ---- device-side HashTable::Convert (HashTable.cpp:75-100) -------------------------------------------

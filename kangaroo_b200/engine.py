@@ -134,11 +134,15 @@ class GPUEngine:
         self.dpMask = dpMask
         self._ck(self._lib.kgx_set_params(self._h, ctypes.c_uint64(dpMask), _p(jd), _p(jx), _p(jy)), "SetParams")
 
-    def SetSymmetry(self, on=True):
-        """USE_SYMMETRY engine mode (reference: compile-time Constants.h:25): lastJump limiter + equivalence-class switch on
-        the device; distances cross the ABI as signed 128-bit values, the wild offset is not applied.  Before SetKangaroos."""
-        self._ck(self._lib.kgx_set_symmetry(self._h, int(bool(on))), "SetSymmetry")
-        self.symmetry = bool(on)
+    SYM_RULES = {None: 0, False: 0, "lastjump": 1, "symclass": 2, True: 2}
+
+    def SetSymmetry(self, rule="symclass"):
+        """USE_SYMMETRY engine mode (reference: compile-time Constants.h:25): equivalence-class switch on the device plus one of
+        the reference's two jump rules -- "symclass" (SolveKeyCPU, Kangaroo.cpp:381-384) or "lastjump" (GPUCompute.h:53-58 =
+        Check.cpp:536-541).  Distances cross the ABI as signed 128-bit values, the wild offset is not applied.  Before SetKangaroos."""
+        mode = self.SYM_RULES[rule]
+        self._ck(self._lib.kgx_set_symmetry(self._h, mode), "SetSymmetry")
+        self.symmetry = mode != 0
 
     def _bias(self, d, kidx0=0):
         """+wildOffset mod n on odd kIdx (GPUEngine.cu:407-411), then truncate to 128 bits like the reference.

@@ -177,20 +177,27 @@ class _Backend:
                                    _ptr(px), _ptr(py), _ptr(d))
         return px, py, d
 
-    def jump_sym(self, px, py, d, last_jump, table, njumps, dp_mask, grp=1024, max_dp=1 << 20):
-        """The symmetric walk of Check.cpp:534-556 (lastJump limiter + class switch), in place; last_jump: uint8 (n,).
+    def jump_sym(self, px, py, d, state, table, njumps, dp_mask, grp=1024, max_dp=1 << 20, rule="lastjump"):
+        """The symmetric walk, in place.  rule "lastjump": Check.cpp:534-556 / GPUCompute.h:53-58 (state = last jump index, uint8,
+        initially 32); rule "symclass": SolveKeyCPU, Kangaroo.cpp:381-384, 422-428 (state = symClass, initially 0).
         -> list of (x, d mod n, kidx, jump) DPs."""
         jd, jpx, jpy = table
         n = px.shape[0]
         dps = (DP * max_dp)()
-        f = self._f("jump_sym"); f.restype = ctypes.c_uint64
-        lj = last_jump.ctypes.data_as(ctypes.c_void_p)
+        st = state.ctypes.data_as(ctypes.c_void_p)
         if self.prefix == "ref_":
-            cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), _ptr(px), _ptr(py), _ptr(d), lj, _ptr(jd), _ptr(jpx), _ptr(jpy),
-                    ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp))
+            if rule == "lastjump":
+                f = self._f("jump_sym"); f.restype = ctypes.c_uint64
+                cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), _ptr(px), _ptr(py), _ptr(d), st, _ptr(jd), _ptr(jpx), _ptr(jpy),
+                        ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp))
+            else:
+                f = self._f("jump_symclass"); f.restype = ctypes.c_uint64
+                cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), ctypes.c_int(grp), _ptr(px), _ptr(py), _ptr(d), st, _ptr(jd), _ptr(jpx),
+                        _ptr(jpy), ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp))
         else:
-            cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), ctypes.c_int(grp), _ptr(px), _ptr(py), _ptr(d), lj, _ptr(jd), _ptr(jpx),
-                    _ptr(jpy), ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp))
+            f = self._f("jump_sym"); f.restype = ctypes.c_uint64
+            cnt = f(ctypes.c_int(n), ctypes.c_int(njumps), ctypes.c_int(grp), _ptr(px), _ptr(py), _ptr(d), st, _ptr(jd), _ptr(jpx),
+                    _ptr(jpy), ctypes.c_uint64(dp_mask), dps, ctypes.c_uint64(max_dp), ctypes.c_int(2 if rule == "symclass" else 1))
         assert cnt <= max_dp, "DP buffer too small"
         return [(from_limbs(dps[i].x), from_limbs(dps[i].d), int(dps[i].kidx), int(dps[i].jump)) for i in range(cnt)]
 

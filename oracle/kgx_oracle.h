@@ -95,7 +95,8 @@ int  kgo_create_jump_table_sym(int range_power, uint64_t *jd, uint64_t *jpx, uin
 void kgo_create_herd_sym(int n, int range_power, const uint64_t range_width_div4[4], const uint64_t keyx[4], const uint64_t keyy[4],
                          int first_type, uint64_t *px, uint64_t *py, uint64_t *d);
 uint64_t kgo_jump_sym(int n, int njumps, int grp, uint64_t *px, uint64_t *py, uint64_t *d, uint8_t *last_jump,
-                      const uint64_t *jd, const uint64_t *jpx, const uint64_t *jpy, uint64_t dp_mask, kgo_dp_t *dps, uint64_t max_dp);
+                      const uint64_t *jd, const uint64_t *jpx, const uint64_t *jpy, uint64_t dp_mask, kgo_dp_t *dps, uint64_t max_dp,
+                      int rule /* 1 = lastJump (Check.cpp:536-541), 2 = symClass (Kangaroo.cpp:381-384) */);
 
 #ifdef __cplusplus
 }

@@ -341,4 +341,55 @@ uint64_t ref_jump_sym(int n, int njumps, uint64_t *px, uint64_t *py, uint64_t *d
   return ndp;
 }
 
+/* SolveKeyCPU's symmetric loop (Kangaroo.cpp:375-433, USE_SYMMETRY branches) through Int / IntGroup: jmp = x mod 16 + 16*symClass,
+ * class switch toggles symClass. */
+uint64_t ref_jump_symclass(int n, int njumps, int grp, uint64_t *px, uint64_t *py, uint64_t *d, uint8_t *symClass,
+                           const uint64_t *jd, const uint64_t *jpx, const uint64_t *jpy, uint64_t dMask, ref_dp_t *dps, uint64_t max_dp) {
+  Int *X = new Int[n], *Y = new Int[n], *D = new Int[n];
+  Int jD[NB_JUMP], jPx[NB_JUMP], jPy[NB_JUMP];
+  for (int i = 0; i < n; i++) { to_int(X[i], px + 4 * i); to_int(Y[i], py + 4 * i); to_int(D[i], d + 4 * i); }
+  for (int i = 0; i < NB_JUMP; i++) { to_int(jD[i], jd + 2 * i, 2); to_int(jPx[i], jpx + 4 * i); to_int(jPy[i], jpy + 4 * i); }
+  uint64_t ndp = 0;
+  Int *dx = new Int[grp];
+  Int dy, rx, ry, _s, _p;
+  for (int run = 0; run < njumps; run++) {
+    for (int g0 = 0; g0 < n; g0 += grp) {
+      int m = (n - g0 < grp) ? (n - g0) : grp;
+      IntGroup *gg = new IntGroup(m);
+      for (int i = 0; i < m; i++) {
+        uint64_t jmp = X[g0 + i].bits64[0] % (NB_JUMP / 2) + (NB_JUMP / 2) * symClass[g0 + i];
+        dx[i].ModSub(&X[g0 + i], &jPx[jmp]);
+      }
+      gg->Set(dx); gg->ModInv();
+      for (int i = 0; i < m; i++) {
+        int k = g0 + i;
+        uint64_t jmp = X[k].bits64[0] % (NB_JUMP / 2) + (NB_JUMP / 2) * symClass[k];
+        Int *p1x = &jPx[jmp], *p1y = &jPy[jmp], *p2x = &X[k], *p2y = &Y[k];
+        dy.ModSub(p2y, p1y);
+        _s.ModMulK1(&dy, &dx[i]);
+        _p.ModSquareK1(&_s);
+        rx.ModSub(&_p, p1x);
+        rx.ModSub(p2x);
+        ry.ModSub(p2x, &rx);
+        ry.ModMulK1(&_s);
+        ry.ModSub(p2y);
+        D[k].ModAddK1order(&jD[jmp]);
+        if (ry.ModPositiveK1()) { D[k].ModNegK1order(); symClass[k] = !symClass[k]; }
+        X[k].Set(&rx); Y[k].Set(&ry);
+        if ((X[k].bits64[3] & dMask) == 0) {
+          if (dps && ndp < max_dp) {
+            from_int(dps[ndp].x, X[k]); from_int(dps[ndp].d, D[k]);
+            dps[ndp].kidx = (uint64_t)k; dps[ndp].jump = (uint32_t)(run + 1); dps[ndp].pad = 0;
+          }
+          ndp++;
+        }
+      }
+      delete gg;
+    }
+  }
+  for (int i = 0; i < n; i++) { from_int(px + 4 * i, X[i]); from_int(py + 4 * i, Y[i]); from_int(d + 4 * i, D[i]); }
+  delete[] dx; delete[] X; delete[] Y; delete[] D;
+  return ndp;
+}
+
 } /* extern "C" */

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from kangaroo_b200 import GPUEngine, NB_RUN  # noqa: E402
 from tests.golden_util import load_cases, arrays  # noqa: E402
 
-KEYS = ("KGX_MODE", "KGX_CFG", "KGX_STREAM_G", "KGX_STREAM_CTAS", "KGX_STREAM_INV")
+KEYS = ("KGX_MODE", "KGX_CFG", "KGX_STREAM_G", "KGX_STREAM_CTAS", "KGX_STREAM_INV", "KGX_STREAM_PF")
 
 
 def main():

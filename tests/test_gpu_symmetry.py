@@ -1,12 +1,15 @@
 """-m gpu: USE_SYMMETRY engine mode.
 
-Parity definition = the symmetric walk the reference's own `Kangaroo::Check` replays on the CPU when it is compiled with
-USE_SYMMETRY (Check.cpp:534-556): jump = x mod 32 bumped when it repeats the kangaroo's previous jump, P += J, d += jD mod n,
-class switch (y > (p-1)/2 -> y = p - y, d = n - d).  Restated in oracle/kgx_oracle.c (kgo_jump_sym), pinned to the reference's
-Int code by tests/test_oracle_vs_ref.py.  Checked here
+The reference has two symmetric jump rules behind its compile-time switch; the engine implements both (include/kgx.h):
+  "lastjump": the device rule (GPUCompute.h:53-58), which Kangaroo::Check replays on the CPU (Check.cpp:534-556): jump = x mod 32
+              bumped when it repeats the kangaroo's previous jump;
+  "symclass": the rule of the working symmetric path, SolveKeyCPU (Kangaroo.cpp:381-384, 422-428): x mod 16 + 16 * symClass.
+Both: P += J, d += jD mod n, class switch (y > (p-1)/2 -> y = p - y, d = n - d).  Restated in oracle/kgx_oracle.c
+(kgo_jump_sym), pinned to the reference's Int / IntGroup code by tests/test_oracle_vs_ref.py.  Checked here
   * through the C ABI on every jump kernel (state + DP multiset, several launches so lastJump persists across launches),
   * through the reference's UNMODIFIED host compiled with -DUSE_SYMMETRY and linked to the engine (build/kangaroo_b200_sym):
-    its own `-check` prints CPU/GPU ok -- which the reference's own symmetric GPU kernel cannot (symmetry),
+    its own `-check` prints CPU/GPU ok (KGX_SYM_RULE=lastjump) -- which the reference's own symmetric GPU kernel cannot
+    (symmetry) -- and in64 is solved with the default symclass rule,
   * statistically: operations per solved key with and without symmetry (the reference's -DSTATS counters), ~1/sqrt(2)."""
 import os
 import re
@@ -32,25 +35,29 @@ def sym_case(oracle, n, rp=64, seed=1, first_type=0):
     return dict(table=table, key=key, px=px, py=py, d=d, n=n, rp=rp)
 
 
+RULES = [("lastjump", 32), ("symclass", 0)]
+
+
+@pytest.mark.parametrize("rule,init", RULES, ids=[r for r, _ in RULES])
 @pytest.mark.parametrize("grid", [(2, 4), (3, 5), (16, 8)])
-def test_symmetric_walk_matches_oracle(oracle, kernel, grid):
+def test_symmetric_walk_matches_oracle(oracle, kernel, grid, rule, init):
     n = grid[0] * grid[1] * 128
     case = sym_case(oracle, n, seed=grid[0] * 10 + grid[1])
     eng = GPUEngine(grid[0], grid[1], 0, 1 << 17, **kernel)
-    eng.SetSymmetry(True)
+    eng.SetSymmetry(rule)
     mask = oracle.dp_mask(7)
     eng.SetParams(mask, *case["table"])
     eng.SetWildOffset(((1 << 64) - 1) >> 2)            # what the host passes (Kangaroo.cpp:548-550); not applied in this mode
     eng.SetKangaroos(case["px"], case["py"], kgo.array_to_ints(case["d"]))
     px, py, d = case["px"].copy(), case["py"].copy(), case["d"].copy()
-    lj = np.full(n, 32, dtype=np.uint8)
+    lj = np.full(n, init, dtype=np.uint8)
     eng.callKernel()
-    for launch in range(3):                            # lastJump must survive between launches
+    for launch in range(3):                            # lastJump / symClass must survive between launches
         found = eng.Launch()
-        want = oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, grp=256, max_dp=1 << 20)
+        want = oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, grp=256, max_dp=1 << 20, rule=rule)
         assert sorted((it.x, it.d, it.kIdx) for it in found) == sorted((x, dd, k) for x, dd, k, j in want), launch
         assert len(found) > 0
-    want = oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, grp=256, max_dp=1 << 20)     # launch 4 is in flight
+    want = oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, grp=256, max_dp=1 << 20, rule=rule)     # launch 4 is in flight
     gx, gy, gd = eng.GetKangaroos()
     assert gx == kgo.array_to_ints(px) and gy == kgo.array_to_ints(py) and gd == kgo.array_to_ints(d)
     half = (kgo.P - 1) // 2
@@ -59,26 +66,27 @@ def test_symmetric_walk_matches_oracle(oracle, kernel, grid):
     eng.sync(); eng.close()
 
 
-def test_symmetric_set_kangaroo_resets_last_jump(oracle, kernel):
-    """SetKangaroo stores lastJump = NB_JUMP for the patched kangaroo (GPUEngine.cu:532-536)."""
+@pytest.mark.parametrize("rule,init", RULES, ids=[r for r, _ in RULES])
+def test_symmetric_set_kangaroo_resets_rule_state(oracle, kernel, rule, init):
+    """SetKangaroo stores lastJump = NB_JUMP (GPUEngine.cu:532-536) / symClass = 0 for the patched kangaroo."""
     n = 2 * 2 * 128
     case = sym_case(oracle, n, seed=5)
     eng = GPUEngine(2, 2, 0, 1 << 16, **kernel)
-    eng.SetSymmetry(True)
+    eng.SetSymmetry(rule)
     mask = oracle.dp_mask(16)
     eng.SetParams(mask, *case["table"])
     eng.SetKangaroos(case["px"], case["py"], kgo.array_to_ints(case["d"]))
     px, py, d = case["px"].copy(), case["py"].copy(), case["d"].copy()
-    lj = np.full(n, 32, dtype=np.uint8)
+    lj = np.full(n, init, dtype=np.uint8)
     eng.callKernel(); eng.Launch(relaunch=False)
-    oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask)
+    oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, rule=rule)
     r = 77
     oracle.rseed(31337)
     nx, ny, nd = oracle.create_herd_sym(1, 64, ((1 << 64) - 1) >> 2, case["key"], r % 2)
-    px[r], py[r], d[r], lj[r] = nx[0], ny[0], nd[0], 32
+    px[r], py[r], d[r], lj[r] = nx[0], ny[0], nd[0], init
     eng.SetKangaroo(r, kgo.from_limbs(nx[0]), kgo.from_limbs(ny[0]), kgo.from_limbs(nd[0]))
     eng.callKernel(); eng.Launch(relaunch=False)
-    oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask)
+    oracle.jump_sym(px, py, d, lj, case["table"], NB_RUN, mask, rule=rule)
     gx, gy, gd = eng.GetKangaroos()
     assert gx == kgo.array_to_ints(px) and gy == kgo.array_to_ints(py) and gd == kgo.array_to_ints(d)
     eng.close()
@@ -96,7 +104,7 @@ def test_symmetric_device_herd_matches_reference_formula(oracle, kernel):
         pt = oracle.ec_mul_g(dv) if i % 2 == 0 else oracle.ec_add(key, oracle.ec_mul_g(dv))
         raw.append(dv if pt[1] == kgo.from_limbs(case["py"][i]) else (kgo.N - dv) % kgo.N)
     eng = GPUEngine(2, 1, 0, 65536, **kernel)
-    eng.SetSymmetry(True)
+    eng.SetSymmetry("symclass")
     eng.CreateHerd(raw, key)
     gx, gy, gd = eng.GetKangaroos()
     assert gx == kgo.array_to_ints(case["px"]) and gy == kgo.array_to_ints(case["py"]) and gd == kgo.array_to_ints(case["d"])
@@ -114,14 +122,18 @@ def run(binary, args, timeout=900, env=None, cwd=None):
 
 @pytest.mark.parametrize("env", [{"KGX_MODE": "stream", "KGX_STREAM_G": "128"}, {"KGX_MODE": "resident"}], ids=["stream128", "resident"])
 def test_reference_check_with_use_symmetry(env):
-    """The reference host compiled with its own USE_SYMMETRY switch, its own Check.cpp:467-621 replay, our engine."""
+    """The reference host compiled with its own USE_SYMMETRY switch, its own Check.cpp:467-621 replay (which follows the DEVICE
+    rule: lastJump), our engine switched to that rule."""
+    env = dict(env, KGX_SYM_RULE="lastjump")
     out = run("kangaroo_b200_sym", ["-gpu", "-check", "-g", "8,128"], env=env)
     assert "CPU/GPU ok" in out, out[-3000:]
     assert "DP Mismatch" not in out and "not ok" not in out
 
 
 def test_symmetric_build_solves_in64():
-    out = run("kangaroo_b200_sym", ["-t", "0", "-gpu", "-g", "64,128", os.path.join(GOLD, "in64.txt")])
+    """Default rule of the symmetric drop-in = symclass (the rule SolveKeyCPU runs).  With the lastjump rule the same program
+    does not terminate on this input: kangaroos fall into fruitless cycles longer than two (measured)."""
+    out = run("kangaroo_b200_sym", ["-t", "0", "-gpu", "-g", "64,128", os.path.join(GOLD, "in64.txt")], timeout=300)
     assert "5B3F38AF935A3640D158E871CE6E9666DB862636383386EE510F18CCC3BD72EB" in out.upper(), out[-2000:]
 
 
@@ -131,7 +143,7 @@ def test_symmetry_gain_in_operations_per_key(tmp_path):
     cfg = os.path.join(GOLD, "in56_64keys.txt")
     avgs = {}
     for binary in ("kangaroo_b200_stats", "kangaroo_b200_sym_stats"):
-        out = run(binary, ["-t", "0", "-gpu", "-g", "8,128", "-d", "4", cfg], timeout=1500, cwd=str(tmp_path))
+        out = run(binary, ["-t", "0", "-gpu", "-g", "8,128", "-d", "4", cfg], timeout=400, cwd=str(tmp_path))
         rows = re.findall(r"^\[\s*(\d+)\] 2\^([0-9.]+) Dead:(\d+) Avg:2\^([0-9.]+) DeadAvg:[0-9.]+ \(([0-9.]+) ([0-9.]+) sqrt\(N\)\)", out, re.M)
         assert len(rows) == 64, out[-2000:]
         assert out.count("Priv: 0x") == 64

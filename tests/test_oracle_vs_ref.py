@@ -122,12 +122,15 @@ def test_symmetric_herd_and_walk_match_reference(oracle, reference):
     half = (kgo.P - 1) // 2
     assert all(kgo.from_limbs(oy[i]) <= half for i in range(n))
     assert any(kgo.from_limbs(od[i]) > kgo.N // 2 for i in range(n))           # some distances went negative (mod n)
-    lo, lr = np.full(n, 32, dtype=np.uint8), np.full(n, 32, dtype=np.uint8)
     mask = oracle.dp_mask(4)
-    do = oracle.jump_sym(ox, oy, od, lo, table, 200, mask, grp=32)
-    dr = reference.jump_sym(rx, ry, rd, lr, table, 200, mask)
-    assert np.array_equal(ox, rx) and np.array_equal(oy, ry) and np.array_equal(od, rd) and np.array_equal(lo, lr)
-    assert sorted(do) == sorted(dr) and len(do) > 500
+    for rule, init in (("lastjump", 32), ("symclass", 0)):
+        lo, lr = np.full(n, init, dtype=np.uint8), np.full(n, init, dtype=np.uint8)
+        do = oracle.jump_sym(ox, oy, od, lo, table, 200, mask, grp=32, rule=rule)
+        dr = reference.jump_sym(rx, ry, rd, lr, table, 200, mask, grp=24, rule=rule)
+        assert np.array_equal(ox, rx) and np.array_equal(oy, ry) and np.array_equal(od, rd) and np.array_equal(lo, lr), rule
+        assert sorted(do) == sorted(dr) and len(do) > 500, rule
+        if rule == "symclass":
+            assert set(np.unique(lo)) == {0, 1}
     # invariant of the class walk: tame x == (d*G).x ; wild x == (key + d*G).x or (key - d*G).x -- a class switch negates
     # the whole point, i.e. d AND the key term, which is why CheckKey tries +-key and the four sign pairs (Kangaroo.cpp:218-253)
     for i in (0, 1, 2, 3, 50, 95):
