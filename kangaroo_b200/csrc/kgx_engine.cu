@@ -30,7 +30,8 @@ struct kgx_engine {
   int streamCtas = 2;
   bool symmetry = false;     // USE_SYMMETRY engine mode (kgx_set_symmetry): class switch + cycle rule, signed distances
   int symRule = 0;           // KGX_SYM_LASTJUMP / KGX_SYM_CLASS
-  int pfDist = 0;            // KGX_STREAM_PF: L2 prefetch distance of the stream kernel (kangaroos)
+  int pfDist = 2;            // KGX_STREAM_PF: L2 prefetch distance of the stream kernel in kangaroos (measured: 0 -> 14.04,
+                             // 2 -> 14.44, 4 -> 14.40, 8 -> 14.24 GJump/s, profiles/r2c_sweep_prefetch.txt)
   uint8_t* aux = nullptr;    // symmetric mode: lastJump per slot
   bool warpInv = true;       // stream kernel: one warp-wide shuffle-butterfly inverse per pass (false: one per thread)
   u32* slab[2] = {nullptr, nullptr};   // DP slabs [count][maxFound*14]

@@ -181,9 +181,12 @@ class Solver:
         t0 = time.time()
         key = None
         steps = 0
+        self.steady = None                      # (time, jumps) after the first 32 steps: NCCL communicator set-up, first table growth
         for s in range(max_steps):
             key = self.step()
             steps += 1
+            if steps == 32:
+                self.steady = (time.time(), self.jumps)
             if verbose and self.rank == 0 and (s % 64 == 63 or self.stop):
                 dt = time.time() - t0
                 print("[%6.1fs] 2^%.2f jumps  %.0f MJump/s  %d DPs  dead %d  ingest %.1f ms/step" %
@@ -192,8 +195,10 @@ class Solver:
             if self.stop:
                 break
         self.eng.sync()
-        self.elapsed = time.time() - t0
+        t1 = time.time()
+        self.elapsed = t1 - t0
         self.steps = steps
+        self.steady_rate = ((self.jumps - self.steady[1]) / (t1 - self.steady[0]) if self.steady and steps > 64 else self.jumps / self.elapsed)
         return key
 
     def close(self):
@@ -222,8 +227,9 @@ def main(argv=None):
                   (s.range_power, s.eng.nbKangaroo, s.world, a.dp, s.dps.threads), flush=True)
         key = s.run(a.max_steps)
         if s.rank == 0:
-            print("Solver rate: %.0f MJump/s over %d steps (%.2f s); rank-0 ingest %.2f ms/step; %d DPs; %d dead kangaroos re-created" %
-                  (s.jumps / s.elapsed / 1e6, s.steps, s.elapsed, 1e3 * s.t_ingest / max(s.steps, 1), len(s.dps), s.same_herd))
+            print("Solver rate: %.0f MJump/s steady state (after the first 32 steps), %.0f MJump/s over all %d steps (%.2f s); "
+                  "rank-0 ingest %.2f ms/step; %d DPs; %d dead kangaroos re-created" %
+                  (s.steady_rate / 1e6, s.jumps / s.elapsed / 1e6, s.steps, s.elapsed, 1e3 * s.t_ingest / max(s.steps, 1), len(s.dps), s.same_herd))
             if a.save_work:
                 s.dps.save_work(a.save_work, a.dp, start, end, pub, total_count=s.jumps, total_time=s.elapsed)
                 print("work file written: %s" % a.save_work)
