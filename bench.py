@@ -429,6 +429,7 @@ def main():
             rt_steps += 1; rt_h2d += n * 80; rt_d2h += n * 80 + 4 + len(items) * 56
         rt_s = time.perf_counter() - t2
 
+    own_kernel_value = float(n) * NB_RUN * steps / dev_s / 1e6        # this rank alone, before the max over ranks
     t = torch.tensor([dev_s, wall, e2e_s, shim_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -439,8 +440,8 @@ def main():
     # one line per rank on stderr (the JSON line on stdout stays rank 0's alone): device, NCCL, this rank's own rates
     nccl_v = ".".join(str(v) for v in torch.cuda.nccl.version()) if world > 1 else "-"
     print("[bench rank %d/%d] cuda:%d %s | NCCL %s | kernel %.1f MJump/s | %d DPs/step | gathered to rank 0: %s"
-          % (rank, world, local_rank, torch.cuda.get_device_name(local_rank), nccl_v, kernel_value, found // max(steps, 1),
-             "yes" if gather is not None else "n/a (single GPU)"), file=sys.stderr, flush=True)
+          % (rank, world, local_rank, torch.cuda.get_device_name(local_rank), nccl_v, own_kernel_value, found // max(steps, 1),
+             "yes" if gather is not None else "n/a (single GPU)") + "\n", file=sys.stderr, end="", flush=True)
     cabi_value = total_jumps / e2e_s / 1e6
     e2e_value = total_jumps / shim_s / 1e6 if shim_s > 0 else cabi_value
 
