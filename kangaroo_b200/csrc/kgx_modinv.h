@@ -167,11 +167,24 @@ KGX_HD void modinv256(uint32_t out[8], const uint32_t in[8]) {
   int32_t eta = -1;
   // full-length updates keep every loop fully unrolled with static register indexing (no local memory);
   // the batch count is data dependent (about 18 for random input; 25 bounds any 256-bit input).
-  for (int it = 0; it < 40; ++it) {
-    t2x2 t;
-    eta = divsteps_30_var(eta, (uint32_t)f.v[0], (uint32_t)g.v[0], &t);
-    update_de_30(&d, &e, &t);
-    update_fg_30<9>(&f, &g, &t);
+  // KGX_INV_UNROLL batches run between two convergence tests: once g == 0 a further batch is the matrix (2^30, 0; 0, 1),
+  // which leaves f and d unchanged (d at most re-normalised by +p), so testing less often is still exact.  The idea was to
+  // let batch k+1's divsteps (which need only the low limbs of f, g) overlap the tail of batch k's 9-limb updates; measured
+  // on a B200 (profiles/r2d_sweep_inverse_unroll.txt) it buys nothing for the warp-uniform inverse of the resident kernel
+  // (6.98 -> 7.02 GJump/s) and costs 1-4 % in the stream kernel (idle batches), so the test stays after every batch.
+#ifndef KGX_INV_UNROLL
+#define KGX_INV_UNROLL 1
+#endif
+  for (int it = 0; it < (26 + KGX_INV_UNROLL - 1) / KGX_INV_UNROLL; ++it) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < KGX_INV_UNROLL; ++k) {
+      t2x2 t;
+      eta = divsteps_30_var(eta, (uint32_t)f.v[0], (uint32_t)g.v[0], &t);
+      update_de_30(&d, &e, &t);
+      update_fg_30<9>(&f, &g, &t);
+    }
     int32_t cond = g.v[0] | g.v[1] | g.v[2] | g.v[3] | g.v[4] | g.v[5] | g.v[6] | g.v[7] | g.v[8];
     if (cond == 0) break;
   }

@@ -23,8 +23,12 @@ def main():
         label, envs, grid = spec.split("|")
         for k in KEYS:
             os.environ.pop(k, None)
+        sym = None
         for kv in filter(None, envs.split(",")):
             k, v = kv.split("=")
+            if k == "SYM":                       # symmetric engine mode: SYM=symclass | SYM=lastjump
+                sym = v
+                continue
             os.environ[k] = v.replace(";", ",")
         gx, gy = (int(v) for v in grid.split(","))
         n = gx * gy * 128
@@ -34,6 +38,8 @@ def main():
         except RuntimeError as e:
             print("%-44s FAILED %s" % (label, e), flush=True)
             continue
+        if sym:
+            eng.SetSymmetry(sym)
         eng.SetParams(0xFFFF000000000000, *case["table"])
         eng.SetKangaroosRaw(sx[idx], sy[idx], np.ascontiguousarray(sd[idx, :2]))
         eng.callKernel()
