@@ -27,6 +27,7 @@ struct kgx_engine {
   uint4* state = nullptr;
   uint4* pre = nullptr;      // streaming mode: prefix-product scratch
   bool streamMode = false;
+  bool tmemMode = false;     // TMEM-backed tile kernel (jump_kernel_tmem<16>)
   int streamCtas = 2;
   bool symmetry = false;     // USE_SYMMETRY engine mode (kgx_set_symmetry): class switch + cycle rule, signed distances
   int symRule = 0;           // KGX_SYM_LASTJUMP / KGX_SYM_CLASS
@@ -166,13 +167,18 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
     const char* mode = getenv("KGX_MODE");
     if (kernel == KGX_KERNEL_STREAM) mode = "stream";
     else if (kernel == KGX_KERNEL_RESIDENT) mode = "resident";
+    else if (kernel == KGX_KERNEL_TMEM) mode = "tmem";
     else if (kernel != KGX_KERNEL_AUTO) { snprintf(g_create_err, sizeof g_create_err, "kgx_create_ex: bad kernel selector %d", kernel); delete e; return nullptr; }
     // default: the streaming kernel for herds of 400 k kangaroos and more (it wants many kangaroos per thread on every
     // SM to amortise the per-thread inverse), the shared-memory tile kernel below that (its inverse is shared by a whole
     // tile, so it keeps ~6.9 GJump/s down to ~270 k kangaroos) -- measured crossover, profiles/r1g_sweep.txt
     e->streamMode = mode ? (strcmp(mode, "stream") == 0) : (KGX_DEFAULT_STREAM != 0 && e->n >= 400000ull);
-    if (mode && strcmp(mode, "stream") && strcmp(mode, "resident")) {
-      snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream or resident"); delete e; return nullptr;
+    if (mode && strcmp(mode, "stream") && strcmp(mode, "resident") && strcmp(mode, "tmem")) {
+      snprintf(g_create_err, sizeof g_create_err, "kgx_create: KGX_MODE must be stream, resident or tmem"); delete e; return nullptr;
+    }
+    if (mode && !strcmp(mode, "tmem")) {
+      e->tmemMode = true;
+      e->T = CfgTm<16>::T; e->K = CfgTm<16>::K; e->smemBytes = CfgTm<16>::SMEM_BYTES; e->ctasPerSM = 2;
     }
     if (e->streamMode) {
       // kangaroos per thread: 128 (the reference's GPU_GRP_SIZE) when the herd fills two CTAs per SM with it; smaller
@@ -228,7 +234,10 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
     cudaMemset(e->prof, 0, 64);
   }
   if ((s = cudaHostAlloc(&e->slabPinned, e->slabBytes, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", s);
-  if (!e->streamMode &&
+  if (e->tmemMode) {
+    if ((s = cudaFuncSetAttribute(jump_kernel_tmem<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smemBytes)) != cudaSuccess)
+      return fail("cudaFuncSetAttribute(smem, tmem kernel)", s);
+  } else if (!e->streamMode &&
       (s = cudaFuncSetAttribute(g_cfgs[e->cfg].kern, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smemBytes)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(smem)", s);
   if ((s = cudaStreamSynchronize(e->stream)) != cudaSuccess) return fail("sync", s);
@@ -236,7 +245,7 @@ kgx_engine* kgx_create_ex(int dev, int groups, int threads_per_group, uint32_t m
 }
 
 uint64_t kgx_num_kangaroos(kgx_engine* e) { return e->n; }
-int kgx_kernel_kind(kgx_engine* e) { return e->streamMode ? KGX_KERNEL_STREAM : KGX_KERNEL_RESIDENT; }
+int kgx_kernel_kind(kgx_engine* e) { return e->streamMode ? KGX_KERNEL_STREAM : (e->tmemMode ? KGX_KERNEL_TMEM : KGX_KERNEL_RESIDENT); }
 uint64_t kgx_memory_bytes(kgx_engine* e) { return e->stateBytes + (e->pre ? e->nPadded * 32 : 0) + 2 * e->slabBytes + JT_WORDS * 4; }
 uint32_t kgx_max_found(kgx_engine* e) { return e->maxFound; }
 float kgx_last_launch_ms(kgx_engine* e) { return e->lastMs; }
@@ -260,6 +269,7 @@ int kgx_set_jumps_per_launch(kgx_engine* e, int n_run) {
 int kgx_set_symmetry(kgx_engine* e, int on) {
   CK(e, cudaSetDevice(e->dev));
   if (e->inflight) { snprintf(e->err, sizeof e->err, "kgx_set_symmetry: a launch is in flight"); return -1; }
+  if (on && e->tmemMode) { snprintf(e->err, sizeof e->err, "kgx_set_symmetry: the TMEM tile kernel has no symmetric instantiation"); return -1; }
   if (on && !e->streamMode && !g_cfgs[e->cfg].kernSym) {
     snprintf(e->err, sizeof e->err, "kgx_set_symmetry: tile geometry %d,%d has no symmetric instantiation", e->T, e->K); return -1;
   }
@@ -443,6 +453,7 @@ int kgx_launch_async(kgx_engine* e) {
       else stream_kernel<128, 2, false, false><<<grid, 128, 0, e->stream>>>(p);
     }
   }
+  else if (e->tmemMode) jump_kernel_tmem<16><<<grid, 128, e->smemBytes, e->stream>>>(p);
   else if (e->symmetry) g_cfgs[e->cfg].kernSym<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   else g_cfgs[e->cfg].kern<<<grid, e->T, e->smemBytes, e->stream>>>(p);
   e->launches++;

@@ -58,7 +58,7 @@ def _p(a):
 
 
 class GPUEngine:
-    KERNELS = {"auto": 0, "stream": 1, "resident": 2}
+    KERNELS = {"auto": 0, "stream": 1, "resident": 2, "tmem": 3}
 
     def __init__(self, nbThreadGroup, nbThreadPerGroup, gpuId=0, maxFound=65536, kernel="auto", stream_g=0):
         """kernel / stream_g are not in the reference constructor (GPUEngine.cu:144): they pin the jump kernel
@@ -82,7 +82,7 @@ class GPUEngine:
         name, sms, _, _, _ = buf.value.decode().split("|")
         self.deviceName = "GPU #%d %s (%sx%d cores) Grid(%dx%d)" % (gpuId, name, sms, 128, nbThreadGroup, nbThreadPerGroup)
         self._items = (Item * maxFound)()
-        self.kernel = {1: "stream", 2: "resident"}[self._lib.kgx_kernel_kind(self._h)]
+        self.kernel = {1: "stream", 2: "resident", 3: "tmem"}[self._lib.kgx_kernel_kind(self._h)]
         self.initialised = True
 
     # -- bookkeeping -------------------------------------------------------------------------------------

@@ -30,7 +30,8 @@ def reference():
 # Every oracle / reference-fixture parity test runs on BOTH jump kernels (kgx_create_ex): "stream128" is the benchmarked
 # configuration (stream kernel, 128 kangaroos per thread, what the default 296x128 grid resolves to), "stream" the
 # adaptive group size small grids get, "resident" the shared-memory tile kernel.
-KERNEL_VARIANTS = {"stream128": dict(kernel="stream", stream_g=128), "stream": dict(kernel="stream"), "resident": dict(kernel="resident")}
+KERNEL_VARIANTS = {"stream128": dict(kernel="stream", stream_g=128), "stream": dict(kernel="stream"), "resident": dict(kernel="resident"),
+                   "tmem": dict(kernel="tmem")}      # tile kernel with y / prefix products in tensor memory (2048-kangaroo tiles)
 
 
 @pytest.fixture(params=sorted(KERNEL_VARIANTS))

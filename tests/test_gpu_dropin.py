@@ -29,8 +29,8 @@ def test_reference_check_gpu_vs_cpu():
     assert "DP Mismatch" not in out and "not ok" not in out
 
 
-@pytest.mark.parametrize("env", [{"KGX_MODE": "stream", "KGX_STREAM_G": "128"}, {"KGX_MODE": "stream"}, {"KGX_MODE": "resident"}],
-                         ids=["stream128", "stream-adaptive", "resident"])
+@pytest.mark.parametrize("env", [{"KGX_MODE": "stream", "KGX_STREAM_G": "128"}, {"KGX_MODE": "resident"}, {"KGX_MODE": "tmem"}],
+                         ids=["stream128", "resident", "tmem"])
 def test_reference_check_largest_grid_on_each_kernel(env):
     """Check.cpp hard-codes dp = 8 and a 65536-record DP buffer (:417, :492), so the largest herd its DP comparison can
     hold is ~2.6e5 kangaroos (expected DPs = nb * 64 / 256 < 65536): `-g 15,128` = 245,760 kangaroos -> ~61.4 k DPs.

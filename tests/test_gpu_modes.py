@@ -17,6 +17,7 @@ VARIANTS = [
     {"KGX_MODE": "resident", "KGX_CFG": "64,5"},
     {"KGX_MODE": "resident", "KGX_CFG": "256,3"},
     {"KGX_MODE": "resident", "KGX_CFG": "32,12"},
+    {"KGX_MODE": "tmem"},
 ]
 
 

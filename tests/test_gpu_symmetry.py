@@ -26,6 +26,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+@pytest.fixture(autouse=True)
+def _no_symmetric_tmem_kernel(request):
+    if "kernel" in request.fixturenames and request.getfixturevalue("kernel").get("kernel") == "tmem":
+        pytest.skip("the TMEM tile kernel has no symmetric instantiation")
+
+
 def sym_case(oracle, n, rp=64, seed=1, first_type=0):
     table = oracle.create_jump_table_sym(rp)
     key = oracle.ec_mul_g(0x5B3F38AF935A3640D158E871CE6E9666DB862636383386EE0000000000123000)
