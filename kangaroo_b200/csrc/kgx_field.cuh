@@ -114,22 +114,25 @@ __device__ __forceinline__ void kgx_merge_eo(u32* w, const u32* E, u32 E15, cons
 // read (no zero-initialisation), every row is one carry chain.
 __device__ __forceinline__ void kgx_mul512(u32* w, const u32* a, const u32* b) {
   u32 E[16], O[15];
+  // A chain whose TOP word is fresh (addend 0) can never carry out: hi(a*b) <= 0xFFFFFFFE, so hi + carry-in fits.  Those rows use
+  // the _x variants (no carry word); the word above is then created by the NEXT row of the same parity, whose top word does
+  // have an addend (_n: carry -> fresh word).  One instruction less per row pair than materialising an always-zero carry.
   kgx_chain_4_8_x(E + 0, b[0], a[0], a[2], a[4], a[6]);   // row 0 even j -> words 0..7   (all new)
   kgx_chain_4_8_x(O + 0, b[0], a[1], a[3], a[5], a[7]);   // row 0 odd  j -> words 1..8   (all new)
-  kgx_chain_4_2_n(E + 2, b[1], a[1], a[3], a[5], a[7]);   // row 1 odd  j -> words 2..9,  E8 E9 new, carry -> E10 new
+  kgx_chain_4_2_x(E + 2, b[1], a[1], a[3], a[5], a[7]);   // row 1 odd  j -> words 2..9,  E8 E9 new (no carry out of a fresh top)
   kgx_chain_4_0_n(O + 0, b[1], a[0], a[2], a[4], a[6]);   // row 1 even j -> words 1..8,  carry -> O8 new
-  kgx_chain_4_0_a(E + 2, b[2], a[0], a[2], a[4], a[6]);   // row 2
-  kgx_chain_4_1_n(O + 2, b[2], a[1], a[3], a[5], a[7]);   //        O9 new, carry -> O10 new
-  kgx_chain_4_1_n(E + 4, b[3], a[1], a[3], a[5], a[7]);   // row 3  E11 new, carry -> E12 new
-  kgx_chain_4_0_a(O + 2, b[3], a[0], a[2], a[4], a[6]);
-  kgx_chain_4_0_a(E + 4, b[4], a[0], a[2], a[4], a[6]);   // row 4
-  kgx_chain_4_1_n(O + 4, b[4], a[1], a[3], a[5], a[7]);   //        O11 new, carry -> O12 new
-  kgx_chain_4_1_n(E + 6, b[5], a[1], a[3], a[5], a[7]);   // row 5  E13 new, carry -> E14 new
-  kgx_chain_4_0_a(O + 4, b[5], a[0], a[2], a[4], a[6]);
-  kgx_chain_4_0_a(E + 6, b[6], a[0], a[2], a[4], a[6]);   // row 6
-  kgx_chain_4_1_n(O + 6, b[6], a[1], a[3], a[5], a[7]);   //        O13 new, carry -> O14 new
-  kgx_chain_4_1_x(E + 8, b[7], a[1], a[3], a[5], a[7]);   // row 7  E15 new, no carry out of word 15
-  kgx_chain_4_0_a(O + 6, b[7], a[0], a[2], a[4], a[6]);
+  kgx_chain_4_0_n(E + 2, b[2], a[0], a[2], a[4], a[6]);   // row 2        words 2..9,  carry -> E10 new
+  kgx_chain_4_1_x(O + 2, b[2], a[1], a[3], a[5], a[7]);   //              O9 new
+  kgx_chain_4_1_x(E + 4, b[3], a[1], a[3], a[5], a[7]);   // row 3        E11 new
+  kgx_chain_4_0_n(O + 2, b[3], a[0], a[2], a[4], a[6]);   //              carry -> O10 new
+  kgx_chain_4_0_n(E + 4, b[4], a[0], a[2], a[4], a[6]);   // row 4        carry -> E12 new
+  kgx_chain_4_1_x(O + 4, b[4], a[1], a[3], a[5], a[7]);   //              O11 new
+  kgx_chain_4_1_x(E + 6, b[5], a[1], a[3], a[5], a[7]);   // row 5        E13 new
+  kgx_chain_4_0_n(O + 4, b[5], a[0], a[2], a[4], a[6]);   //              carry -> O12 new
+  kgx_chain_4_0_n(E + 6, b[6], a[0], a[2], a[4], a[6]);   // row 6        carry -> E14 new
+  kgx_chain_4_1_x(O + 6, b[6], a[1], a[3], a[5], a[7]);   //              O13 new
+  kgx_chain_4_1_x(E + 8, b[7], a[1], a[3], a[5], a[7]);   // row 7        E15 new, no carry out of word 15
+  kgx_chain_4_0_n(O + 6, b[7], a[0], a[2], a[4], a[6]);   //              carry -> O14 new
   kgx_merge_eo(w, E, E[15], O);
 }
 
@@ -144,19 +147,22 @@ __device__ __forceinline__ void fe_mul(u32* r, const u32* a, const u32* b) {
 __device__ __forceinline__ void kgx_sqr512(u32* w, const u32* a) {
   u32 E[16], O[15];
   // E[i] sits at word i, O[i] at word i+1; product a_i*a_j lands at word i+j.  E0 E1 are never written (zero).
+  // (same rule as kgx_mul512: a chain with a fresh top word cannot carry out -> _x; the word above is created by the next chain
+  //  of that parity with a real top addend -> _n.  E14 and O14 are never written: they are zero.)
   kgx_chain_4_8_x(O + 0, a[0], a[1], a[3], a[5], a[7]);   // 0x{1,3,5,7} -> words 1,3,5,7   O0..O7 new
-  kgx_chain_3_6_n(E + 2, a[0], a[2], a[4], a[6]);         // 0x{2,4,6}   -> words 2,4,6     E2..E7 new, E8 = 0
+  kgx_chain_3_6_x(E + 2, a[0], a[2], a[4], a[6]);         // 0x{2,4,6}   -> words 2,4,6     E2..E7 new
   kgx_chain_3_0_n(O + 2, a[1], a[2], a[4], a[6]);         // 1x{2,4,6}   -> words 3,5,7     carry -> O8 new
-  kgx_chain_3_1_n(E + 4, a[1], a[3], a[5], a[7]);         // 1x{3,5,7}   -> words 4,6,8     E9 new, carry -> E10 new
-  kgx_chain_3_1_n(O + 4, a[2], a[3], a[5], a[7]);         // 2x{3,5,7}   -> words 5,7,9     O9 new, carry -> O10 new
-  kgx_chain_2_0_a(E + 6, a[2], a[4], a[6]);               // 2x{4,6}     -> words 6,8
-  kgx_chain_2_0_a(O + 6, a[3], a[4], a[6]);               // 3x{4,6}     -> words 7,9
-  kgx_chain_2_1_n(E + 8, a[3], a[5], a[7]);               // 3x{5,7}     -> words 8,10      E11 new, carry -> E12 new
-  kgx_chain_2_1_n(O + 8, a[4], a[5], a[7]);               // 4x{5,7}     -> words 9,11      O11 new, carry -> O12 new
-  kgx_chain_1_0_a(E + 10, a[4], a[6]);                    // 4x6         -> word 10
-  kgx_chain_1_0_a(O + 10, a[5], a[6]);                    // 5x6         -> word 11
-  kgx_chain_1_1_n(E + 12, a[5], a[7]);                    // 5x7         -> word 12         E13 new, carry -> E14 new
-  kgx_chain_1_1_n(O + 12, a[6], a[7]);                    // 6x7         -> word 13         O13 new, carry -> O14 new
+  kgx_chain_3_2_x(E + 4, a[1], a[3], a[5], a[7]);         // 1x{3,5,7}   -> words 4,6,8     E8 E9 new
+  kgx_chain_3_1_x(O + 4, a[2], a[3], a[5], a[7]);         // 2x{3,5,7}   -> words 5,7,9     O9 new
+  kgx_chain_2_0_n(E + 6, a[2], a[4], a[6]);               // 2x{4,6}     -> words 6,8       carry -> E10 new
+  kgx_chain_2_0_n(O + 6, a[3], a[4], a[6]);               // 3x{4,6}     -> words 7,9       carry -> O10 new
+  kgx_chain_2_1_x(E + 8, a[3], a[5], a[7]);               // 3x{5,7}     -> words 8,10      E11 new
+  kgx_chain_2_1_x(O + 8, a[4], a[5], a[7]);               // 4x{5,7}     -> words 9,11      O11 new
+  kgx_chain_1_0_n(E + 10, a[4], a[6]);                    // 4x6         -> word 10         carry -> E12 new
+  kgx_chain_1_0_n(O + 10, a[5], a[6]);                    // 5x6         -> word 11         carry -> O12 new
+  kgx_chain_1_1_x(E + 12, a[5], a[7]);                    // 5x7         -> word 12         E13 new
+  kgx_chain_1_1_x(O + 12, a[6], a[7]);                    // 6x7         -> word 13         O13 new
+  E[14] = 0; O[14] = 0;
   // C = E + (O << 32), words 1..15 (words 0 and, from E, 1 are zero)
   u32 c[16];
   c[1] = O[0];
