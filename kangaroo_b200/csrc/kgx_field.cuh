@@ -28,20 +28,13 @@ __device__ __forceinline__ void kgx_fold(u32* r, u32* w) {
 #pragma unroll
   for (int i = 0; i < 8; i++) e[i] = w[i];
   kgx_chain_4_0_n(e, c, w[8], w[10], w[12], w[14]);
-  // O' = {h1,h3,h5,h7} * c at words 1..8, then + h (the 2^32 part of 0x1000003D1, also at words 1..8)
+  // O'' = h (the 2^32 part of 0x1000003D1, words 1..8) + {h1,h3,h5,h7} * c (pairs at words 1,3,5,7): the products are
+  // accumulated straight INTO a copy of h -- one chain, no separate 9-instruction addition.  Every multiplicand h_(2k+1) is read
+  // for the last time by the instruction that overwrites its own accumulator word, so the copy may share its registers.
   u32 o[9];
-  kgx_chain_4_8_x(o, c, w[9], w[11], w[13], w[15]);
-  asm("add.cc.u32  %0, %0, %9;\n\t"
-      "addc.cc.u32 %1, %1, %10;\n\t"
-      "addc.cc.u32 %2, %2, %11;\n\t"
-      "addc.cc.u32 %3, %3, %12;\n\t"
-      "addc.cc.u32 %4, %4, %13;\n\t"
-      "addc.cc.u32 %5, %5, %14;\n\t"
-      "addc.cc.u32 %6, %6, %15;\n\t"
-      "addc.cc.u32 %7, %7, %16;\n\t"
-      "addc.u32    %8, 0, 0;"
-      : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "=&r"(o[8])
-      : "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]));
+#pragma unroll
+  for (int i = 0; i < 8; i++) o[i] = w[8 + i];
+  kgx_chain_4_0_n(o, c, w[9], w[11], w[13], w[15]);
   // R1 = E' + (O'' << 32): words 1..9
   asm("add.cc.u32  %0, %0, %9;\n\t"
       "addc.cc.u32 %1, %1, %10;\n\t"
