@@ -256,6 +256,7 @@ def shim_run(prep, gx, gy, local_rank, dp, warmup, steps):
         if p.returncode != 0 or not line:
             raise RuntimeError("kgx_shim_bench failed: " + (p.stdout + p.stderr)[-500:])
         r = json.loads(line[-1])
+        shim_run.last = r
         return r["seconds"], r["items"], r["upload_s"]
     finally:
         for f in (tab_path, herd_path):
@@ -494,7 +495,8 @@ def main():
                          "marshalling + ModSubK1order per record (GPUEngine.cu:607-679); host-clock around the K calls, max over ranks"
                          if shim_s > 0 else
                          "kgx_collect(relaunch=1) loop through the C ABI with host item buffers (C++ harness not built)"),
-                 "one_time_upload_s": shim_upload},
+                 "one_time_upload_s": shim_upload,
+                 "get_kangaroos_s": getattr(shim_run, "last", {}).get("get_kangaroos_s")},
             e2e_c_abi={"value": cabi_value, "unit": "MJump/s", "d2h_bytes_per_step": d2h / max(steps, 1),
                        "how": "kgx_collect(relaunch=1) from Python/ctypes into a host array of 56-byte items: the C ABI alone, no Int marshalling"},
             roofline={"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s (32x32->64 multiply-adds)",

@@ -66,8 +66,12 @@ int main(int argc, char** argv) {
   // each Launch waited for one kernel (the one started by the previous call) and read its DPs back: exactly K kernels and K
   // readbacks are inside the timed region; the launch started by the last call is outside (the destructor waits for it)
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  printf("{\"steps\": %d, \"seconds\": %.6f, \"items\": %llu, \"kangaroos\": %zu, \"upload_s\": %.3f, \"chk\": %llu}\n", steps, sec,
-         (unsigned long long)items, n, upload, (unsigned long long)chk);
+  // checkpoint read-out (Kangaroo.cpp:618-626): GetKangaroos waits for the launch in flight, copies the herd out and marshals it into Int
+  t0 = std::chrono::steady_clock::now();
+  eng.GetKangaroos(px, py, d);
+  const double getk = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("{\"steps\": %d, \"seconds\": %.6f, \"items\": %llu, \"kangaroos\": %zu, \"upload_s\": %.3f, \"get_kangaroos_s\": %.3f, \"chk\": %llu}\n",
+         steps, sec, (unsigned long long)items, n, upload, getk, (unsigned long long)chk);
   delete[] px; delete[] py; delete[] d;
   return 0;
 }
