@@ -42,7 +42,7 @@ void       kgi_reset(kgi_table* t);                 /* HashTable::Reset */
 uint64_t   kgi_count(kgi_table* t);                 /* HashTable::GetNbItem */
 int        kgi_threads(kgi_table* t);
 
-/* Insert n records (dp40: n x 40 bytes) tagged with `rank`.  Events (resets, collisions) are appended to ev[0..cap);
+/* Insert n records (dp40: n x 40 bytes) tagged with `rank`.  One caller at a time per table (the workers are the parallelism).  Events (resets, collisions) are appended to ev[0..cap);
  * *n_ev = number of events produced (may exceed cap: the excess is dropped, resets are best-effort like the reference's).
  * Returns 0, or -1 on a malformed record (h >= 2^18). */
 int kgi_add(kgi_table* t, const void* dp40, uint32_t n, uint32_t rank, kgi_event* ev, uint32_t cap, uint32_t* n_ev);

@@ -5,15 +5,20 @@
 //
 //   reference      : every thread owns 128 kangaroos in LOCAL memory (18.5 KB stack/thread): px/py/dx/subp arrays are
 //                    re-read and re-written through L1/L2 several times per jump (~416 B/jump), three passes.
-//   stream_kernel  : (default for herds >= 4e5 kangaroos, kgx_engine.cu) every thread owns a private group of G kangaroos that live in HBM as
+//   stream_kernel  : (default for herds >= 4e5 kangaroos, kgx_engine.cu) every thread owns G kangaroos that live in HBM as
 //                    coalesced 16-byte SoA chunks; ONE fused pass per jump reads prefix/x/y/d and writes x'/y'/d'/next
-//                    prefix (224 B/jump) with the next kangaroo prefetched into a second register buffer; no barriers,
-//                    no cross-thread traffic; per-thread variable-time safegcd inverse once per G jumps.
+//                    prefix (224 B/jump) with the next kangaroo prefetched into a second register buffer and the pair two
+//                    trips ahead pulled into L2; no barriers.  Group inverse once per G jumps: the 32 lane products of a warp
+//                    are multiplied by a shuffle butterfly and ONE warp-uniform safegcd inverse serves 32*G kangaroos
+//                    (WARPINV), or every thread inverts its own product (short groups).
 //   jump_kernel    : (resident; default for small herds) a CTA of T threads owns a tile of T*K kangaroos whose whole
 //                    state stays in SHARED memory for all NB_RUN jumps of a launch (HBM 2.5 B/jump).  The batch inverse
 //                    spans the tile: per-thread chains -> per-lane chains across the warps -> XOR-butterfly product over
 //                    the 32 lanes with warp shuffles -> ONE warp-uniform inverse per tile per jump -> back down the tree;
 //                    several CTAs per SM overlap one tile's serial inverse with another's parallel phase.
+//   jump_kernel_tmem : (opt-in) the resident kernel with y and the prefix products in TENSOR MEMORY (tcgen05.alloc/ld/st as a
+//                    lane-private store): 2048-kangaroo tiles, 4096 resident kangaroos per SM.
+//   SYM instantiations of the first two add the reference's USE_SYMMETRY paths (class switch + lastJump / symClass rule).
 //
 //   Both use the same fused per-kangaroo pass: back-substitution of this jump's inverse, the affine add, the
 //   distance update, the DP test, and the *next* jump's dx / prefix product (accumulated in the order of this pass,
