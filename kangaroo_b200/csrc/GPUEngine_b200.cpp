@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <vector>
 #include "GPU/GPUEngine.h"
 #include "../../include/kgx.h"
@@ -130,27 +132,45 @@ void GPUEngine::SetParams(uint64_t dpMask, Int* distance, Int* px, Int* py) {  /
   if (kgx_set_params(KGX(inputKangaroo), dpMask, jd, jx, jy) != 0) printf("GPUEngine: SetParams: %s\n", kgx_last_error(KGX(inputKangaroo)));
 }
 
+// Int <-> limb marshalling of a whole herd (4.85 M kangaroos x 3 Int on the default grid) on several host threads: the
+// checkpoint path (Kangaroo.cpp:618-626) parks the GPU thread on GetKangaroos, so its duration is GPU idle time.
+template <typename F>
+static void parallel_for(uint64_t n, F body) {
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt == 0 ? 1 : (nt > 16 ? 16 : nt);
+  if (n < 65536) nt = 1;
+  std::vector<std::thread> th;
+  const uint64_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back([=] { const uint64_t a = t * chunk, b = a + chunk < n ? a + chunk : n; for (uint64_t i = a; i < b; i++) body(i); });
+  for (uint64_t i = 0; i < (chunk < n ? chunk : n); i++) body(i);
+  for (auto& x : th) x.join();
+}
+
 void GPUEngine::SetKangaroos(Int* px, Int* py, Int* d) {                        // GPUEngine.cu:381-433
   if (!inputKangaroo) return;
   const uint64_t n = kgx_num_kangaroos(KGX(inputKangaroo));
-  std::vector<uint64_t> ax(n * 4), ay(n * 4), ad(n * 2);
-  for (uint64_t i = 0; i < n; i++) {
-    int_to_limbs(&ax[4 * i], &px[i], 4); int_to_limbs(&ay[4 * i], &py[i], 4);
-    dist_to_abi(&ad[2 * i], &d[i], i % 2 == WILD, &wildOffset);
-  }
-  if (kgx_upload(KGX(inputKangaroo), ax.data(), ay.data(), ad.data()) != 0) printf("GPUEngine: SetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo)));
+  std::unique_ptr<uint64_t[]> ax(new uint64_t[n * 4]), ay(new uint64_t[n * 4]), ad(new uint64_t[n * 2]);
+  Int* wo = &wildOffset;
+  uint64_t *bx = ax.get(), *by = ay.get(), *bd = ad.get();
+  parallel_for(n, [=](uint64_t i) {
+    int_to_limbs(bx + 4 * i, &px[i], 4); int_to_limbs(by + 4 * i, &py[i], 4);
+    dist_to_abi(bd + 2 * i, &d[i], i % 2 == WILD, wo);
+  });
+  if (kgx_upload(KGX(inputKangaroo), bx, by, bd) != 0) printf("GPUEngine: SetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo)));
 }
 
 void GPUEngine::GetKangaroos(Int* px, Int* py, Int* d) {                        // GPUEngine.cu:435-491
   if (!inputKangaroo) { printf("GPUEngine: GetKangaroos: Cannot retreive kangaroos, mem has been freed\n"); return; }
   const uint64_t n = kgx_num_kangaroos(KGX(inputKangaroo));
-  std::vector<uint64_t> ax(n * 4), ay(n * 4), ad(n * 2);
-  if (kgx_download(KGX(inputKangaroo), ax.data(), ay.data(), ad.data()) != 0) { printf("GPUEngine: GetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo))); return; }
-  for (uint64_t i = 0; i < n; i++) {
-    for (int k = 0; k < 4; k++) { px[i].bits64[k] = ax[4 * i + k]; py[i].bits64[k] = ay[4 * i + k]; }
+  std::unique_ptr<uint64_t[]> ax(new uint64_t[n * 4]), ay(new uint64_t[n * 4]), ad(new uint64_t[n * 2]);
+  uint64_t *bx = ax.get(), *by = ay.get(), *bd = ad.get();
+  if (kgx_download(KGX(inputKangaroo), bx, by, bd) != 0) { printf("GPUEngine: GetKangaroos: %s\n", kgx_last_error(KGX(inputKangaroo))); return; }
+  Int* wo = &wildOffset;
+  parallel_for(n, [=](uint64_t i) {
+    for (int k = 0; k < 4; k++) { px[i].bits64[k] = bx[4 * i + k]; py[i].bits64[k] = by[4 * i + k]; }
     px[i].bits64[4] = 0; py[i].bits64[4] = 0;
-    dist_from_abi(&d[i], &ad[2 * i], i % 2 == WILD, &wildOffset);
-  }
+    dist_from_abi(&d[i], bd + 2 * i, i % 2 == WILD, wo);
+  });
 }
 
 void GPUEngine::SetKangaroo(uint64_t kIdx, Int* px, Int* py, Int* d) {          // GPUEngine.cu:493-538

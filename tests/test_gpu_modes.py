@@ -31,15 +31,15 @@ def test_variant_bit_exact(env):
 
 def test_stream_and_resident_agree_over_a_long_walk(monkeypatch):
     """Cross-validation at a scale the CPU oracle cannot reach: 1,048,576 kangaroos x 100 launches (6400 jumps each) on the
-    two independent kernel implementations (different memory layout, different batch-inverse topology) must end in
-    bit-identical states and produce the same DP multiset."""
+    three independent kernel implementations (different memory layout, different batch-inverse topology; the tile kernels loop
+    over several tiles per CTA here) must end in bit-identical states and produce the same DP multiset."""
     import numpy as np
     from kangaroo_b200 import GPUEngine, random_herd_arrays
     from tests.golden_util import load_cases
     case = [c for c in load_cases() if c["range_power"] == 80][0]
     sc, d128 = random_herd_arrays(64 * 128 * 128, 80, case["width_div2"], np.random.Generator(np.random.PCG64(2024)))
     results = {}
-    for mode in ("stream", "resident"):
+    for mode in ("stream", "resident", "tmem"):
         monkeypatch.setenv("KGX_MODE", mode)
         eng = GPUEngine(64, 128, 0, 1 << 17)
         eng.SetParams(0xFFFFF00000000000, *case["table"])          # dp = 20
@@ -53,6 +53,8 @@ def test_stream_and_resident_agree_over_a_long_walk(monkeypatch):
         ax, ay, ad = eng.GetKangaroosRaw()
         results[mode] = (ax, ay, ad, sorted(dps))
         eng.close()
-    a, b = results["stream"], results["resident"]
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-    assert a[3] == b[3] and len(a[3]) > 3000
+    a = results["stream"]
+    for other in ("resident", "tmem"):
+        b = results[other]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), other
+        assert a[3] == b[3] and len(a[3]) > 3000, other

@@ -117,6 +117,36 @@ def test_symmetric_device_herd_matches_reference_formula(oracle, kernel):
     eng.close()
 
 
+def test_symmetric_device_hash_convert(oracle, kernel):
+    """kgx_convert_dps in symmetric mode: the record's distance is a signed 128-bit value (no wild offset); the 40-byte DP
+    must equal HashTable::Convert(x, d mod n, type) (HashTable.cpp:75-100)."""
+    import torch
+    from kangaroo_b200.dist import SlabView, decode_dp40
+    n = 2 * 4 * 128
+    case = sym_case(oracle, n, seed=21)
+    eng = GPUEngine(2, 4, 0, 65536, **kernel)
+    eng.SetSymmetry("symclass")
+    eng.SetParams(oracle.dp_mask(5), *case["table"])
+    eng.SetKangaroos(case["px"], case["py"], kgo.array_to_ints(case["d"]))
+    eng.callKernel()
+    found = eng.Launch(relaunch=False)
+    ptr = eng.convert_dps_device_ptr()
+    raw = torch.as_tensor(SlabView(ptr, 4 + 65536 * 40), device="cuda").cpu()
+    cnt = int.from_bytes(bytes(raw[:4].numpy().tobytes()), "little")
+    assert cnt == len(found) > 100
+    want = {}
+    for it in found:
+        h, X, D = oracle.hash_convert(it.x, it.d, it.kIdx % 2)
+        want[(it.kIdx & 0xFFFFFFFF, X)] = (h, D)
+    n_neg = 0
+    for kidx, h, x, dist, ktype in decode_dp40(raw[4:4 + cnt * 40]):
+        D = (abs(dist) & ((1 << 126) - 1)) | ((1 << 127) if dist < 0 else 0) | (ktype << 126)
+        assert (h, D) == want[(kidx, x)]
+        n_neg += dist < 0
+    assert n_neg > 0
+    eng.close()
+
+
 def run(binary, args, timeout=900, env=None, cwd=None):
     exe = os.path.join(ROOT, "build", binary)
     if not os.path.exists(exe):
