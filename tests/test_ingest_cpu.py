@@ -170,3 +170,37 @@ def test_insert_rate_is_reported(oracle, capsys):
         with capsys.disabled():
             print("\n[ingest] %d threads: %.2f M DP/s (%d records, batches of 50000)" % (threads, n / dt / 1e6, n))
         t.close()
+
+
+def test_small_search_end_to_end_on_the_cpu(oracle):
+    """The whole host side of a search without a GPU: herds and jumps from the oracle (SolveKeyCPU's loop, Kangaroo.cpp:375-433),
+    every distinguished point through kgi_add into the reference's HashTable, same-herd hits answered by re-creating that
+    kangaroo (Kangaroo.cpp:601-609), the tame/wild collision resolved by the reference's CheckKey -> the private key."""
+    from kangaroo_b200.ingest import DPTable, EV_RESET, EV_COLLISION
+    rp, dp_bits, n = 32, 5, 256
+    start = 0x49DCCFD96DC5DF56487436F5A1B18C4F5D34F65DDB48CB5E0000000000000000
+    oracle.rseed(0x600DCAFE)
+    priv = start + oracle.rand_bits(rp)
+    key = ec.add(ec.mul(priv), ec.neg(ec.mul(start)))
+    table = oracle.create_jump_table(rp)
+    wd2 = 1 << (rp - 1)
+    px, py, d = oracle.create_herd(n, rp, wd2, key)
+    mask = oracle.dp_mask(dp_bits)
+    t = DPTable(threads=2, max_events=1 << 14)
+    found, jumps, resets = None, 0, 0
+    for _ in range(400):                                                  # 400 x 256 x 64 = 6.5 M jumps >> 2 sqrt(2^32)
+        dps = oracle.jump_cpu(px, py, d, table, 64, mask)
+        jumps += n * 64
+        ev = t.add_dp40(b"".join(rec40(oracle, x, dist, kidx & 1, kidx) for x, dist, kidx, _ in dps))
+        for kind, _, kidx, d_old, d_new in ev:
+            if kind == EV_COLLISION:
+                found = t.resolve(d_old, d_new, key, start)
+            elif kind == EV_RESET:
+                resets += 1
+                nx, ny, nd = oracle.create_herd(1, rp, wd2, key, first_type=kidx & 1)
+                px[kidx], py[kidx], d[kidx] = nx[0], ny[0], nd[0]
+        if found is not None:
+            break
+    t.close()
+    print("solved after %d jumps (2 sqrt(N) = %d), %d resets" % (jumps, 2 << (rp // 2), resets))
+    assert found == priv
