@@ -80,6 +80,11 @@ __device__ __forceinline__ void lds_jp(u32* r, const u32* tab, u32 j) {
 #pragma unroll
   for (int w = 0; w < 8; w++) r[w] = tab[w * 32 + j];
 }
+// 128-bit variant for the stream kernel: table as uint4 jt[5][32] = {jpx lo, jpx hi, jpy lo, jpy hi, jd}, one LDS.128 per half
+__device__ __forceinline__ void lds_jp4(u32* r, const uint4* tab, u32 j) {
+  const uint4 a = tab[j], b = tab[32 + j];
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
 __device__ __forceinline__ void shfl_xor_fe(u32* r, const u32* a, int mask) {
 #pragma unroll
   for (int w = 0; w < 8; w++) r[w] = __shfl_xor_sync(0xffffffffu, a[w], mask);
@@ -522,19 +527,19 @@ __device__ __noinline__ void emit_dp_from_state(const LaunchParams& p, const uin
 // One kangaroo of the fused pass (see the file header): back-substitute, jump, start the next chain.  Branch-free:
 // returns whether the new point is distinguished (x' and d' are in the state chunks for emit_dp_from_state).
 template <int T, bool SYM>
-__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, uint8_t* ag, const u32* jpx, const u32* jpy,
-                                            const u32* jd, u32* I, u32* P, const u32 mlo, const u32 mhi, const int rule) {
+__device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint4* pg, uint8_t* ag, const uint4* jt, u32* I, u32* P,
+                                            const u32 mlo, const u32 mhi, const int rule) {
   u32 x[8], y[8], jx[8], jy[8], dx[8], inv[8], s[8], rx[8], ry[8], d[4];
   unpack8(x, cur.x0, cur.x1);
   unpack8(inv, cur.p0, cur.p1);
   const u32 j = jump_index<SYM>(x[0], cur.lj, rule);
   u32 auxn = 0;
-  lds_jp(jx, jpx, j);
+  lds_jp4(jx, jt, j);
   fe_sub(dx, x, jx);
   fe_mul(inv, inv, I);                     // 1/dx
   fe_mul(I, I, dx);                        // strip this dx from the running inverse (unused after the last one)
   unpack8(y, cur.y0, cur.y1);
-  lds_jp(jy, jpy, j);
+  lds_jp4(jy, jt + 64, j);
   fe_sub(s, y, jy);
   fe_mul(s, s, inv);                       // s = dy/dx
   fe_sqr(rx, s);
@@ -544,7 +549,8 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
   fe_mul(ry, ry, s);
   fe_sub(ry, ry, y);                       // ry = s (x - rx) - y
   d[0] = cur.d.x; d[1] = cur.d.y; d[2] = cur.d.z; d[3] = cur.d.w;
-  d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+  const uint4 jd = jt[128 + j];
+  d128_add(d, jd.x, jd.y, jd.z, jd.w);
   if (SYM) {                               // equivalence class switch (Check.cpp:551-556): y > (p-1)/2 -> (x, p - y), d -> -d
     const u32 neg = fe_gt_half_mask(ry);
     fe_cneg(ry, neg);
@@ -558,7 +564,7 @@ __device__ __forceinline__ bool stream_body(const KangLoad& cur, uint4* sg, uint
   sg[3 * T] = make_uint4(ry[4], ry[5], ry[6], ry[7]);
   sg[4 * T] = make_uint4(d[0], d[1], d[2], d[3]);
   // next jump's dx and prefix product, accumulated in THIS order (P starts at 1 for the first kangaroo of a pass)
-  lds_jp(jx, jpx, jump_index<SYM>(rx[0], auxn, rule));
+  lds_jp4(jx, jt, jump_index<SYM>(rx[0], auxn, rule));
   fe_sub(dx, rx, jx);
   pg[0] = make_uint4(P[0], P[1], P[2], P[3]);
   pg[T] = make_uint4(P[4], P[5], P[6], P[7]);
@@ -590,13 +596,13 @@ __device__ __forceinline__ void stream_group_inverse(u32* I, const u32* P) {
 template <int T, int CTAS, bool WARPINV, bool SYM>
 __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
   const int G = p.G;     // even: the fused pass is unrolled by two
-  __shared__ u32 sJ[JT_WORDS];
-  const u32* jpx = sJ;
-  const u32* jpy = sJ + 8 * 32;
-  const u32* jd = sJ + 16 * 32;
+  __shared__ uint4 jt[5 * 32];            // {jpx lo, jpx hi, jpy lo, jpy hi, jd} x 32 jumps: one LDS.128 per half element
   const int t = threadIdx.x;
   const u32 mlo = (u32)p.dpMask, mhi = (u32)(p.dpMask >> 32);
-  for (int i = t; i < JT_WORDS; i += T) sJ[i] = p.jtab[i];
+  for (int i = t; i < 5 * 32; i += T) {   // p.jtab is word-major: word w of jump j at [w * 32 + j]
+    const int q = i >> 5, j = i & 31;
+    jt[i] = make_uint4(p.jtab[(4 * q) * 32 + j], p.jtab[(4 * q + 1) * 32 + j], p.jtab[(4 * q + 2) * 32 + j], p.jtab[(4 * q + 3) * 32 + j]);
+  }
   __syncthreads();
 
   for (u32 tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
 #pragma unroll 1
       for (int g = 0; g < G; g++) {
         unpack8(x, st[(g * CHUNKS + 0) * T], st[(g * CHUNKS + 1) * T]);
-        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)au[(size_t)g * T] : 0u, p.symRule));
+        lds_jp4(jx, jt, jump_index<SYM>(x[0], SYM ? (u32)au[(size_t)g * T] : 0u, p.symRule));
         fe_sub(dx, x, jx);
         pr[(g * 2) * T] = make_uint4(P[0], P[1], P[2], P[3]); pr[(g * 2 + 1) * T] = make_uint4(P[4], P[5], P[6], P[7]);
         fe_mul(P, P, dx);
@@ -648,9 +654,9 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + dp + T));
         }
         stream_load<T, SYM>(B, sg + ds, pg + dp, ag + dk);
-        const bool ha = stream_body<T, SYM>(A, sg, pg, ag, jpx, jpy, jd, I, P, mlo, mhi, p.symRule);
+        const bool ha = stream_body<T, SYM>(A, sg, pg, ag, jt, I, P, mlo, mhi, p.symRule);
         if (i + 2 < G) stream_load<T, SYM>(A, sg + 2 * ds, pg + 2 * dp, ag + 2 * dk);
-        const bool hb = stream_body<T, SYM>(B, sg + ds, pg + dp, ag + dk, jpx, jpy, jd, I, P, mlo, mhi, p.symRule);
+        const bool hb = stream_body<T, SYM>(B, sg + ds, pg + dp, ag + dk, jt, I, P, mlo, mhi, p.symRule);
         if (ha) emit_dp_from_state<T>(p, sg, kidx);
         if (hb) emit_dp_from_state<T>(p, sg + ds, kidx + dk);
         sg += 2 * ds; pg += 2 * dp; kidx += 2 * dk;
