@@ -287,15 +287,18 @@ int kgx_set_symmetry(kgx_engine* e, int on) {
 }
 int kgx_get_symmetry(kgx_engine* e) { return e->symmetry ? e->symRule : 0; }
 
+// word w (0..7 jpx, 8..15 jpy, 16..19 jd) of jump j in the device table: uint4 jt[w / 4][j], component w % 4 (kgx_kernel.cuh)
+static inline int jt_word(int w, int j) { return ((w >> 2) * 32 + j) * 4 + (w & 3); }
+
 int kgx_set_params(kgx_engine* e, uint64_t dp_mask, const uint64_t* jd, const uint64_t* jpx, const uint64_t* jpy) {
   CK(e, cudaSetDevice(e->dev));
   u32 tab[JT_WORDS];
   for (int j = 0; j < 32; j++) {
     for (int w = 0; w < 8; w++) {
-      tab[w * 32 + j] = (u32)(jpx[4 * j + w / 2] >> (32 * (w & 1)));
-      tab[(8 + w) * 32 + j] = (u32)(jpy[4 * j + w / 2] >> (32 * (w & 1)));
+      tab[jt_word(w, j)] = (u32)(jpx[4 * j + w / 2] >> (32 * (w & 1)));
+      tab[jt_word(8 + w, j)] = (u32)(jpy[4 * j + w / 2] >> (32 * (w & 1)));
     }
-    for (int w = 0; w < 4; w++) tab[(16 + w) * 32 + j] = (u32)(jd[2 * j + w / 2] >> (32 * (w & 1)));
+    for (int w = 0; w < 4; w++) tab[jt_word(16 + w, j)] = (u32)(jd[2 * j + w / 2] >> (32 * (w & 1)));
   }
   CK(e, cudaStreamSynchronize(e->stream));   // a running kernel may still read the old table
   CK(e, cudaMemcpy(e->jtab, tab, sizeof tab, cudaMemcpyHostToDevice));

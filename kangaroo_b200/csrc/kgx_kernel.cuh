@@ -30,7 +30,7 @@
 namespace kgx {
 
 constexpr int CHUNKS = 5;         // 16-byte chunks per kangaroo in HBM: x0 x1 y0 y1 d
-constexpr int JT_WORDS = 20 * 32; // jump table: jpx[8][32] jpy[8][32] jd[4][32], word-major (bank = jump index)
+constexpr int JT_WORDS = 20 * 32; // jump table as uint4 jt[5][32] = {jpx lo, jpx hi, jpy lo, jpy hi, jd} x 32 jumps: one LDS.128 per half element
 
 // Tile geometry: T threads per CTA (W = T/32 warps), K kangaroos per thread.  Shared memory (uint4 units):
 //   X[K][2][T] Y[K][2][T] P[K][2][T] D[K][T] TOT[2][T] then the jump table (u32 view).
@@ -76,11 +76,7 @@ __device__ __forceinline__ void sts_fe(uint4* base, int idx0, int idx1, const u3
 __device__ __forceinline__ void unpack8(u32* r, const uint4& a, const uint4& b) {
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
-__device__ __forceinline__ void lds_jp(u32* r, const u32* tab, u32 j) {
-#pragma unroll
-  for (int w = 0; w < 8; w++) r[w] = tab[w * 32 + j];
-}
-// 128-bit variant for the stream kernel: table as uint4 jt[5][32] = {jpx lo, jpx hi, jpy lo, jpy hi, jd}, one LDS.128 per half
+// one half (4 limbs) of a jump-table element per LDS.128: tab[j] = low half, tab[32 + j] = high half
 __device__ __forceinline__ void lds_jp4(u32* r, const uint4* tab, u32 j) {
   const uint4 a = tab[j], b = tab[32 + j];
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
@@ -165,15 +161,12 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
   uint4* sP = smem + C::S_P;
   uint4* sD = smem + C::S_D;
   uint4* sTot = smem + C::S_TOT;
-  u32* sJ = reinterpret_cast<u32*>(smem + C::S_JT);
-  const u32* jpx = sJ;
-  const u32* jpy = sJ + 8 * 32;
-  const u32* jd = sJ + 16 * 32;
+  uint4* jt = smem + C::S_JT;
   const int t = threadIdx.x;
   const int lane = t & 31;
   const u32 mlo = (u32)p.dpMask, mhi = (u32)(p.dpMask >> 32);
 
-  for (int i = t; i < JT_WORDS; i += T) sJ[i] = p.jtab[i];
+  for (int i = t; i < JT_WORDS; i += T) reinterpret_cast<u32*>(jt)[i] = p.jtab[i];
 
   for (u32 tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
     __syncthreads();   // jump table visible; previous tile's shared state fully consumed
@@ -194,7 +187,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
 #pragma unroll 1
       for (int g = 0; g < K; g++) {
         lds_fe(x, sX, (g * 2) * T + t, (g * 2 + 1) * T + t);
-        lds_jp(jx, jpx, jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u, p.symRule));
+        lds_jp4(jx, jt, jump_index<SYM>(x[0], SYM ? (u32)sL[g * T + t] : 0u, p.symRule));
         fe_sub(dx, x, jx);
         if (g == 0) {
           u32 one[8]; fe_set_one(one);
@@ -232,12 +225,12 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
         const u32 aux0 = SYM ? (u32)sL[g * T + t] : 0u;
         const u32 j = jump_index<SYM>(x[0], aux0, p.symRule);
         u32 aux1 = 0;
-        lds_jp(jx, jpx, j);
+        lds_jp4(jx, jt, j);
         fe_sub(dx, x, jx);
         fe_mul(inv, inv, I);                     // 1/dx
         if (i != K - 1) fe_mul(I, I, dx);        // strip this dx from the running inverse
         lds_fe(y, sY, i0, i1);
-        lds_jp(jy, jpy, j);
+        lds_jp4(jy, jt + 64, j);
         fe_sub(s, y, jy);                        // dy
         fe_mul(s, s, inv);                       // s = dy/dx
         fe_sqr(rx, s);                           // s^2
@@ -248,7 +241,8 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
         fe_sub(ry, ry, y);                       // ry = s (x - rx) - y
         uint4 dv = sD[g * T + t];
         u32 d[4] = {dv.x, dv.y, dv.z, dv.w};
-        d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+        const uint4 jd = jt[128 + j];
+        d128_add(d, jd.x, jd.y, jd.z, jd.w);
         if (SYM) {                               // class switch (Check.cpp:551-556), see stream_body
           const u32 neg = fe_gt_half_mask(ry);
           fe_cneg(ry, neg);
@@ -273,7 +267,7 @@ __global__ void __launch_bounds__(T, Cfg<T, K>::CTAS_PER_SM) jump_kernel(LaunchP
           }
         }
         if (!last) {                             // next jump's dx and prefix, accumulated in THIS order
-          lds_jp(jx, jpx, jump_index<SYM>(rx[0], aux1, p.symRule));
+          lds_jp4(jx, jt, jump_index<SYM>(rx[0], aux1, p.symRule));
           fe_sub(dx, rx, jx);
           if (i == 0) {
             u32 one[8]; fe_set_one(one);
@@ -345,16 +339,13 @@ __global__ void __launch_bounds__(128, 2) jump_kernel_tmem(LaunchParams p) {
   uint4* sX = smem + C::S_X;
   uint4* sD = smem + C::S_D;
   uint4* sTot = smem + C::S_TOT;
-  u32* sJ = reinterpret_cast<u32*>(smem + C::S_JT);
+  uint4* jt = smem + C::S_JT;
   u32* slot = reinterpret_cast<u32*>(reinterpret_cast<uint8_t*>(smem) + C::SLOT_OFF);
-  const u32* jpx = sJ;
-  const u32* jpy = sJ + 8 * 32;
-  const u32* jd = sJ + 16 * 32;
   const int t = threadIdx.x;
   const int lane = t & 31;
   const u32 mlo = (u32)p.dpMask, mhi = (u32)(p.dpMask >> 32);
 
-  for (int i = t; i < JT_WORDS; i += T) sJ[i] = p.jtab[i];
+  for (int i = t; i < JT_WORDS; i += T) reinterpret_cast<u32*>(jt)[i] = p.jtab[i];
   if (t < 32) {                                  // one warp allocates this CTA's columns and lets the next CTA allocate
     const u32 slot_addr = (u32)__cvta_generic_to_shared(slot);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(slot_addr), "r"((u32)C::COLS) : "memory");
@@ -387,7 +378,7 @@ __global__ void __launch_bounds__(128, 2) jump_kernel_tmem(LaunchParams p) {
 #pragma unroll 1
       for (int g = 0; g < K; g++) {
         lds_fe(x, sX, (g * 2) * T + t, (g * 2 + 1) * T + t);
-        lds_jp(jx, jpx, x[0] & 31u);
+        lds_jp4(jx, jt, x[0] & 31u);
         fe_sub(dx, x, jx);
         if (g == 0) {
           u32 one[8]; fe_set_one(one);
@@ -417,12 +408,12 @@ __global__ void __launch_bounds__(128, 2) jump_kernel_tmem(LaunchParams p) {
         lds_fe(x, sX, i0, i1);
         tmem_ld_fe(inv, KGX_TM_P(g));            // prefix of this kangaroo
         const u32 j = x[0] & 31u;
-        lds_jp(jx, jpx, j);
+        lds_jp4(jx, jt, j);
         fe_sub(dx, x, jx);
         fe_mul(inv, inv, I);                     // 1/dx
         if (i != K - 1) fe_mul(I, I, dx);
         tmem_ld_fe(y, KGX_TM_Y(g));
-        lds_jp(jy, jpy, j);
+        lds_jp4(jy, jt + 64, j);
         fe_sub(s, y, jy);
         fe_mul(s, s, inv);
         fe_sqr(rx, s);
@@ -435,7 +426,8 @@ __global__ void __launch_bounds__(128, 2) jump_kernel_tmem(LaunchParams p) {
         tmem_st_fe(KGX_TM_Y(g), ry);
         uint4 dv = sD[g * T + t];
         u32 d[4] = {dv.x, dv.y, dv.z, dv.w};
-        d128_add(d, jd[j], jd[32 + j], jd[64 + j], jd[96 + j]);
+        const uint4 jd = jt[128 + j];
+        d128_add(d, jd.x, jd.y, jd.z, jd.w);
         sD[g * T + t] = make_uint4(d[0], d[1], d[2], d[3]);
         if (((rx[7] & mhi) | (rx[6] & mlo)) == 0u) {
           const u64 kidx = (u64)tile * TILE + (u64)g * T + (u64)t;
@@ -451,7 +443,7 @@ __global__ void __launch_bounds__(128, 2) jump_kernel_tmem(LaunchParams p) {
           }
         }
         if (!last) {
-          lds_jp(jx, jpx, rx[0] & 31u);
+          lds_jp4(jx, jt, rx[0] & 31u);
           fe_sub(dx, rx, jx);
           if (i == 0) {
             u32 one[8]; fe_set_one(one);
@@ -513,12 +505,12 @@ __device__ __forceinline__ void stream_load(KangLoad& k, const uint4* sg, const 
 // written (same thread, program order): the hot loop keeps neither x' nor d' alive for it -- no local-memory home, no
 // extra registers.
 template <int T>
-__device__ __noinline__ void emit_dp_from_state(const LaunchParams& p, const uint4* sg, u64 kidx) {
-  if (kidx >= p.nKangaroos) return;                    // padding slot
-  const u32 pos = atomicAdd(p.out, 1u);
-  if (pos >= p.maxFound) return;                       // GPUEngine.cu:641-648: counted, not stored
+__device__ __noinline__ void emit_dp_from_state(u32* out, const u32 maxFound, const u64 nKangaroos, const uint4* sg, u64 kidx) {
+  if (kidx >= nKangaroos) return;                      // padding slot
+  const u32 pos = atomicAdd(out, 1u);
+  if (pos >= maxFound) return;                         // GPUEngine.cu:641-648: counted, not stored
   const uint4 x0 = sg[0], x1 = sg[T], d = sg[4 * T];
-  u32* o = p.out + 1 + (size_t)pos * 14;
+  u32* o = out + 1 + (size_t)pos * 14;
   o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
   o[8] = d.x; o[9] = d.y; o[10] = d.z; o[11] = d.w;
   o[12] = (u32)kidx; o[13] = (u32)(kidx >> 32);
@@ -596,13 +588,10 @@ __device__ __forceinline__ void stream_group_inverse(u32* I, const u32* P) {
 template <int T, int CTAS, bool WARPINV, bool SYM>
 __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
   const int G = p.G;     // even: the fused pass is unrolled by two
-  __shared__ uint4 jt[5 * 32];            // {jpx lo, jpx hi, jpy lo, jpy hi, jd} x 32 jumps: one LDS.128 per half element
-  const int t = threadIdx.x;
+  __shared__ uint4 jt[JT_WORDS / 4];
+  const int t = threadIdx.x, lane = t & 31;
   const u32 mlo = (u32)p.dpMask, mhi = (u32)(p.dpMask >> 32);
-  for (int i = t; i < 5 * 32; i += T) {   // p.jtab is word-major: word w of jump j at [w * 32 + j]
-    const int q = i >> 5, j = i & 31;
-    jt[i] = make_uint4(p.jtab[(4 * q) * 32 + j], p.jtab[(4 * q + 1) * 32 + j], p.jtab[(4 * q + 2) * 32 + j], p.jtab[(4 * q + 3) * 32 + j]);
-  }
+  for (int i = t; i < JT_WORDS; i += T) reinterpret_cast<u32*>(jt)[i] = p.jtab[i];
   __syncthreads();
 
   for (u32 tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
@@ -638,27 +627,30 @@ __global__ void __launch_bounds__(T, CTAS) stream_kernel(LaunchParams p) {
       u64 kidx = kbase + (u64)g0 * T;
       KangLoad A, B;                              // ping-pong prefetch buffers (no register copies)
       stream_load<T, SYM>(A, sg, pg, ag);
+      // L2 prefetch of the pair p.pfDist trips ahead (no registers held): a pair is 14 planes (2 x {x lo, x hi, y lo, y hi, d} of the
+      // state, 2 x {lo, hi} of the prefix products) of 512 B per warp = 56 lines of 128 B.  Each LANE asks for a different line --
+      // lane -> (plane lane/4, line lane%4) -- so two instructions cover the pair instead of one per plane (14).
+      const int pl = lane >> 2;
+      const ptrdiff_t lineOff = (ptrdiff_t)((lane & 3) * 8) - lane;                       // uint4 units, from this thread's own address
+      const uint4* q1 = pl < 5 ? sg + (ptrdiff_t)p.pfDist * ds + pl * T + lineOff         // first kangaroo: 5 state planes,
+                               : pg + (ptrdiff_t)p.pfDist * dp + (pl < 7 ? (pl - 5) * T : dp) + lineOff;   // its 2 prefix planes, the second's low one
+      const uint4* q2 = pl < 5 ? sg + (ptrdiff_t)(p.pfDist + 1) * ds + pl * T + lineOff   // second kangaroo: 5 state planes,
+                               : pg + (ptrdiff_t)(p.pfDist + 1) * dp + T + lineOff;       // its high prefix plane (lanes 20..23)
+      const ptrdiff_t qs = 2 * (pl < 5 ? ds : dp);
+      const bool q2on = pl < 6;
 #pragma unroll 1
       for (int i = 0; i < G; i += 2) {
-        if (p.pfDist > 0 && i + p.pfDist + 1 < G) {      // pull the pair two trips ahead into L2 (no registers held)
-          const uint4* fs = sg + (ptrdiff_t)p.pfDist * ds;
-          const uint4* fp = pg + (ptrdiff_t)p.pfDist * dp;
-#pragma unroll
-          for (int c = 0; c < CHUNKS; c++) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(fs + c * T));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(fs + ds + c * T));
-          }
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + T));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + dp));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + dp + T));
+        if (p.pfDist > 0 && i + p.pfDist + 1 < G) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
+          if (q2on) asm volatile("prefetch.global.L2 [%0];" ::"l"(q2));
         }
+        q1 += qs; q2 += qs;
         stream_load<T, SYM>(B, sg + ds, pg + dp, ag + dk);
         const bool ha = stream_body<T, SYM>(A, sg, pg, ag, jt, I, P, mlo, mhi, p.symRule);
         if (i + 2 < G) stream_load<T, SYM>(A, sg + 2 * ds, pg + 2 * dp, ag + 2 * dk);
         const bool hb = stream_body<T, SYM>(B, sg + ds, pg + dp, ag + dk, jt, I, P, mlo, mhi, p.symRule);
-        if (ha) emit_dp_from_state<T>(p, sg, kidx);
-        if (hb) emit_dp_from_state<T>(p, sg + ds, kidx + dk);
+        if (ha) emit_dp_from_state<T>(p.out, p.maxFound, p.nKangaroos, sg, kidx);
+        if (hb) emit_dp_from_state<T>(p.out, p.maxFound, p.nKangaroos, sg + ds, kidx + dk);
         sg += 2 * ds; pg += 2 * dp; kidx += 2 * dk;
         if (SYM) ag += 2 * dk;
       }
